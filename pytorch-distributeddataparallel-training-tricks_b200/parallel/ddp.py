@@ -1,0 +1,151 @@
+"""``DistributedDataParallel`` -- the framework's own data-parallel wrapper.
+
+Drop-in for the reference's call site ``DDP(model, device_ids=[r], output_device=r)``
+(utils/train.py:61) with the behaviours the reference depended on (SURVEY.md C13,
+N2, N5):
+
+* construction verifies parameter shapes across ranks and broadcasts rank 0's
+  parameters and buffers to everyone;
+* every grad-enabled forward re-broadcasts the module's buffers (BatchNorm running
+  statistics) from rank 0 -- as one coalesced transfer, not one call per dtype;
+* backward overlaps one all-reduce per gradient bucket with the rest of backward
+  and leaves ``param.grad`` holding the average over ranks;
+* ``.module`` is the wrapped model; ``state_dict`` keys gain the ``module.`` prefix
+  exactly like torch's wrapper; ``no_sync()`` is supported (the reference never
+  used it, torch users expect it).
+
+Design differences (B200-first): parameters and gradients are re-homed onto flat
+arenas so buckets are slices (no copies), the bucket plan is static (no rebuild, no
+index broadcast), and with ``comm="fused"`` the all-reduce is our NVLink kernel
+that also folds in the loss-scale division and the overflow check.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .arena import FlatArena
+from .buckets import plan_buckets
+from .reducer import ProcessGroupBackend, Reducer
+
+
+def _flat_broadcast(tensors: List[torch.Tensor], src: int, group) -> None:
+    """Broadcast tensors from ``src`` coalesced per dtype (one collective per dtype)."""
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, items in by_dtype.items():
+        flat = torch.cat([t.detach().reshape(-1) for t in items])
+        dist.broadcast(flat, src=src, group=group)
+        offset = 0
+        with torch.no_grad():
+            for t in items:
+                n = t.numel()
+                t.copy_(flat[offset: offset + n].view(t.shape))
+                offset += n
+
+
+class DistributedDataParallel(nn.Module):
+    def __init__(self, module: nn.Module, device_ids=None, output_device=None,
+                 broadcast_buffers: bool = True, bucket_cap_mb: float = 25.0,
+                 process_group=None, comm: str = "auto", find_unused_parameters: bool = False,
+                 gradient_as_bucket_view: bool = True):
+        super().__init__()
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DistributedDataParallel needs an initialised process group")
+        if find_unused_parameters:
+            raise NotImplementedError("find_unused_parameters is not supported (static bucket plan)")
+        self.module = module
+        self.process_group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.broadcast_buffers = broadcast_buffers
+        self.device_ids = device_ids
+        self.output_device = output_device
+        self._params = [p for p in module.parameters()]
+        if not self._params:
+            raise ValueError("module has no parameters to synchronise")
+        self.device = self._params[0].device
+        self._verify_shapes()
+
+        # ---- comm back end ----------------------------------------------------------
+        backend = None
+        grad_alloc = None
+        self.comm = "pg"
+        if comm in ("auto", "fused") and self.device.type == "cuda" and self.world_size > 1:
+            try:
+                from .symm import FusedNvlinkBackend
+                backend = FusedNvlinkBackend(self.device, process_group)
+                grad_alloc = backend.allocate
+                self.comm = "fused"
+            except Exception as exc:  # symmetric memory / extension unavailable
+                if comm == "fused":
+                    raise
+                import warnings
+                warnings.warn(f"fused NVLink all-reduce unavailable ({exc}); using process-group collectives")
+        if backend is None:
+            backend = ProcessGroupBackend(process_group)
+
+        # ---- arenas, buckets, initial sync, reducer ---------------------------------
+        self.buckets = plan_buckets(self._params, bucket_cap_mb)
+        self.arena = FlatArena(self._params, self.buckets, grad_allocator=grad_alloc)
+        if hasattr(backend, "bind"):
+            backend.bind(self.arena)
+        self._sync_module_states()
+        self.reducer = Reducer(self.arena, backend)
+        self._buffers_dirty = True  # mirrors torch's require_forward_param_sync
+        from ..amp import current_state
+        current_state().reducers.append(self.reducer)
+        fused_opt_hook = getattr(module, "_ddpt_on_arena", None)
+        if fused_opt_hook is not None:
+            fused_opt_hook(self.arena)
+
+    # -- construction helpers ------------------------------------------------------------
+    def _verify_shapes(self) -> None:
+        mine = [tuple(p.shape) for p in self._params]
+        gathered: List[Optional[list]] = [None] * self.world_size
+        dist.all_gather_object(gathered, mine, group=self.process_group)
+        for r, other in enumerate(gathered):
+            if other != mine:
+                raise RuntimeError(f"parameter shapes differ between rank {self.rank} and rank {r}")
+
+    def _sync_module_states(self) -> None:
+        with torch.no_grad():
+            dist.broadcast(self.arena.param_arena, src=0, group=self.process_group)
+        self._sync_buffers()
+
+    def _sync_buffers(self) -> None:
+        bufs = [b for b in self.module.buffers()]
+        if bufs:
+            _flat_broadcast(bufs, 0, self.process_group)
+
+    # -- forward / backward ----------------------------------------------------------------
+    def forward(self, *inputs, **kwargs):
+        grad_on = torch.is_grad_enabled()
+        if self.broadcast_buffers and self.world_size > 1 and (grad_on or self._buffers_dirty):
+            self._sync_buffers()
+        self._buffers_dirty = grad_on
+        if grad_on and self.reducer.require_sync:
+            self.reducer.prepare_for_backward()
+        return self.module(*inputs, **kwargs)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old = self.reducer.require_sync
+        self.reducer.require_sync = False
+        try:
+            yield
+        finally:
+            self.reducer.require_sync = old
+
+    # -- conveniences ---------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = False) -> None:  # arena-backed grads are zeroed in place
+        self.arena.zero_grads()
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        return self

@@ -1,0 +1,60 @@
+"""C3: sampler parity with torch DistributedSampler, IDX reader, batch loader tails."""
+import os
+
+import pytest
+import torch
+from torch.utils.data.distributed import DistributedSampler
+
+from ddpt_b200.data import BatchLoader, ShardedSampler, load_mnist, synthetic_mnist
+
+
+@pytest.mark.parametrize("n,world", [(60000, 2), (60000, 8), (1001, 4), (10, 3)])
+@pytest.mark.parametrize("epoch", [0, 3])
+def test_sampler_matches_torch(n, world, epoch):
+    ds = range(n)
+    for rank in range(world):
+        ref = DistributedSampler(ds, num_replicas=world, rank=rank)
+        ref.set_epoch(epoch)
+        ours = ShardedSampler(n, num_replicas=world, rank=rank)
+        ours.set_epoch(epoch)
+        assert list(ref) == ours.indices().tolist()
+        assert len(ref) == len(ours)
+
+
+def test_sampler_no_shuffle_and_drop_last():
+    for kw in (dict(shuffle=False), dict(drop_last=True), dict(shuffle=False, drop_last=True)):
+        ref = DistributedSampler(range(103), num_replicas=4, rank=1, **kw)
+        ours = ShardedSampler(103, num_replicas=4, rank=1, **kw)
+        assert list(ref) == ours.indices().tolist()
+
+
+def test_tail_batches_like_reference():
+    data = synthetic_mnist(60000)
+    for world, steps, tail in [(1, 59, 608), (2, 30, 304), (4, 15, 664), (8, 8, 332)]:
+        loader = BatchLoader(data, 1024, ShardedSampler(60000, world, 0), mode="torch")
+        assert len(loader) == steps
+        sizes = [img.shape[0] for img, _ in loader]
+        assert sizes[-1] == tail and all(s == 1024 for s in sizes[:-1])
+
+
+def test_loader_values_are_totensor_equivalent():
+    data = synthetic_mnist(300)
+    loader = BatchLoader(data, 128, None, mode="torch")
+    img, tgt = next(iter(loader))
+    assert img.shape == (128, 1, 28, 28) and img.dtype == torch.float32 and tgt.dtype == torch.int64
+    torch.testing.assert_close(img[:, 0], data.images[:128].float() / 255.0, rtol=0, atol=0)
+    assert torch.equal(tgt, data.labels[:128])
+
+
+def test_idx_reader_on_reference_dataset(reference_root):
+    root = os.path.join(reference_root, "datasets")
+    train, test = load_mnist(root, True), load_mnist(root, False)
+    assert train.images.shape == (60000, 28, 28) and train.images.dtype == torch.uint8
+    assert test.images.shape == (10000, 28, 28) and train.labels[:5].tolist() == [5, 0, 4, 1, 9]
+    processed = torch.load(os.path.join(root, "MNIST/processed/training.pt"), weights_only=True)
+    assert torch.equal(processed[0], train.images) and torch.equal(processed[1], train.labels)
+
+
+def test_missing_dataset_message(tmp_path):
+    with pytest.raises(FileNotFoundError, match="--synthetic"):
+        load_mnist(str(tmp_path))
