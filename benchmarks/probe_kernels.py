@@ -1,0 +1,130 @@
+"""Micro-benchmarks of the tcgen05 kernels on Toy_Net shapes + a library (cuDNN/cuBLAS) step baseline.
+
+    python benchmarks/probe_kernels.py [--out gpurun_out/probe_kernels.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def timeit(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    times.sort()
+    return times[len(times) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/probe_kernels.json")
+    ap.add_argument("--batch", type=int, default=1024)
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    res = {"device": torch.cuda.get_device_name(0), "batch": args.batch}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    B = args.batch
+    try:
+        from ddpt_b200.ops import gemm
+        rows = []
+        for name, (h, w, ci, co) in {"conv.3": (26, 26, 64, 128), "conv.7": (12, 12, 128, 256),
+                                     "conv.10": (10, 10, 256, 512)}.items():
+            x = torch.randn(B, h, w, ci, device="cuda").bfloat16()
+            wk = (torch.randn(co, 9 * ci, device="cuda") * 0.05).bfloat16()
+            dy = torch.randn(B, h - 2, w - 2, co, device="cuda").bfloat16()
+            flops = 2.0 * B * (h - 2) * (w - 2) * co * ci * 9
+            for bn in (64, 128, 256):
+                if co % bn == 0:
+                    t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn), flush=flush)
+                    rows.append(dict(op=f"{name}.fwd", block_n=bn, ms=t, tflops=flops / t / 1e9))
+                if ci % bn == 0:
+                    t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn), flush=flush)
+                    rows.append(dict(op=f"{name}.dgrad", block_n=bn, ms=t, tflops=flops / t / 1e9))
+                    dw = torch.zeros(co, 3, 3, ci, device="cuda")
+                    t = timeit(lambda: gemm.conv_wgrad(dy, x, 3, 3, out=dw, block_n=bn), flush=flush)
+                    rows.append(dict(op=f"{name}.wgrad", block_n=bn, ms=t, tflops=flops / t / 1e9))
+            # library reference for the same layer (channels_last bf16)
+            xn = x.permute(0, 3, 1, 2)
+            wn = wk.view(co, 3, 3, ci).permute(0, 3, 1, 2)
+            t = timeit(lambda: F.conv2d(xn, wn), flush=flush)
+            rows.append(dict(op=f"{name}.fwd.cudnn", ms=t, tflops=flops / t / 1e9))
+        x = torch.randn(B, 8192, device="cuda").bfloat16()
+        w1 = (torch.randn(512, 8192, device="cuda") * 0.01).bfloat16()
+        dy = torch.randn(B, 512, device="cuda").bfloat16()
+        fl = 2.0 * B * 8192 * 512
+        for bn, sk in ((64, 1), (128, 1), (128, 4), (64, 2)):
+            t = timeit(lambda: gemm.linear_fwd(x, w1, None, out_dtype=torch.float32, split_k=sk, block_n=bn), flush=flush)
+            rows.append(dict(op="dense.1.fwd", block_n=bn, split_k=sk, ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: gemm.linear_dgrad(dy, w1), flush=flush)
+        rows.append(dict(op="dense.1.dgrad", ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: gemm.linear_wgrad(dy, x), flush=flush)
+        rows.append(dict(op="dense.1.wgrad", ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: x @ w1.t(), flush=flush)
+        rows.append(dict(op="dense.1.fwd.cublas", ms=t, tflops=fl / t / 1e9))
+        res["kernels"] = rows
+    except Exception as exc:  # keep the library baseline even if our kernels fail
+        import traceback
+        res["kernel_error"] = traceback.format_exc()
+
+    # library baseline: torch Toy_Net, bf16 autocast, channels_last, fwd+bwd+SGD step, B per GPU
+    try:
+        from ddpt_b200.models import Toy_Net
+        model = Toy_Net().cuda().to(memory_format=torch.channels_last)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True)
+        xin = torch.rand(B, 1, 28, 28, device="cuda")
+        tgt = torch.randint(0, 10, (B,), device="cuda")
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = model.forward_reference(xin)
+            loss = F.cross_entropy(out.float(), tgt) / B
+            loss.backward()
+            opt.step()
+        t = timeit(step, iters=20, warmup=5)
+        res["library_step_ms"] = t
+        res["library_img_per_s"] = B / t * 1e3
+        g = torch.cuda.CUDAGraph()
+        opt2 = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, capturable=False)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(s)
+        try:
+            with torch.cuda.graph(g):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = model.forward_reference(xin)
+                loss = F.cross_entropy(out.float(), tgt) / B
+                loss.backward()
+            t = timeit(g.replay, iters=20, warmup=3)
+            res["library_graph_fwdbwd_ms"] = t
+        except Exception as exc:
+            res["library_graph_error"] = repr(exc)
+    except Exception:
+        import traceback
+        res["library_error"] = traceback.format_exc()
+    with open(args.out, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1)[:6000])
+
+
+if __name__ == "__main__":
+    main()

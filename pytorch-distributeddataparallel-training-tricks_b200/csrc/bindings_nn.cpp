@@ -1,0 +1,168 @@
+// Bindings for the bandwidth-bound Toy_Net kernels (csrc/nn/toynet_elementwise.cu).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "include/ddpt_toynet.h"
+
+namespace {
+
+cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
+const __nv_bfloat16* bf(const at::Tensor& t) { return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr()); }
+__nv_bfloat16* bfm(at::Tensor& t) { return reinterpret_cast<__nv_bfloat16*>(t.data_ptr()); }
+
+void need(const at::Tensor& t, at::ScalarType dt, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == dt && t.is_contiguous(), name, ": expected contiguous CUDA ", dt);
+}
+
+int64_t conv0_partial_rows() { return ddpt::conv0_partial_rows(); }
+int64_t bn_bwd_partial_rows() { return ddpt::bn_bwd_partial_rows(); }
+
+int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y, c10::optional<at::Tensor> partials) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
+  TORCH_CHECK(x.numel() % (28 * 28) == 0, "conv0 expects 28x28 single-channel images");
+  need(weight, at::kFloat, "weight"); need(bias, at::kFloat, "bias"); need(y, at::kBFloat16, "y");
+  const int batch = (int)(x.numel() / (28 * 28));
+  TORCH_CHECK(weight.numel() == 64 * 9 && bias.numel() == 64 && y.numel() == (int64_t)batch * 26 * 26 * 64);
+  c10::cuda::CUDAGuard g(x.device());
+  float* part = nullptr;
+  if (partials.has_value()) {
+    need(*partials, at::kFloat, "partials");
+    TORCH_CHECK(partials->numel() >= ddpt::conv0_partial_rows() * 2 * 64);
+    part = partials->data_ptr<float>();
+  }
+  return ddpt::launch_conv0_fwd(x.data_ptr(), x.scalar_type() == at::kByte, weight.data_ptr<float>(),
+                                bias.data_ptr<float>(), bfm(y), part, batch, cur());
+}
+
+void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
+  need(dy, at::kBFloat16, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
+  const int batch = (int)(x.numel() / (28 * 28));
+  TORCH_CHECK(dy.numel() == (int64_t)batch * 26 * 26 * 64 && dw.numel() == 576 && db.numel() == 64);
+  c10::cuda::CUDAGuard g(x.device());
+  ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
+                           db.data_ptr<float>(), batch, cur());
+}
+
+// coeffs: float [4][C] = scale, shift, mean, invstd
+void bn_finalize(at::Tensor partials, int64_t num_partials, double count, at::Tensor gamma, at::Tensor beta,
+                 double eps, double momentum, at::Tensor coeffs, c10::optional<at::Tensor> running_mean,
+                 c10::optional<at::Tensor> running_var, c10::optional<at::Tensor> nbt) {
+  need(partials, at::kFloat, "partials"); need(gamma, at::kFloat, "gamma"); need(beta, at::kFloat, "beta");
+  need(coeffs, at::kFloat, "coeffs");
+  const int c = (int)gamma.numel();
+  TORCH_CHECK(coeffs.numel() >= 4 * c && partials.numel() >= num_partials * 2 * c);
+  c10::cuda::CUDAGuard g(gamma.device());
+  float* co = coeffs.data_ptr<float>();
+  ddpt::BnCoeffs out{co, co + c, co + 2 * c, co + 3 * c};
+  long long* n = nullptr;
+  if (nbt.has_value()) { TORCH_CHECK(nbt->scalar_type() == at::kLong); n = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
+  ddpt::launch_bn_finalize(partials.data_ptr<float>(), (int)num_partials, c, count, gamma.data_ptr<float>(),
+                           beta.data_ptr<float>(), (float)eps, (float)momentum, out,
+                           running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
+                           running_var.has_value() ? running_var->data_ptr<float>() : nullptr, n, cur());
+}
+
+void bn_eval_coeffs(at::Tensor gamma, at::Tensor beta, at::Tensor running_mean, at::Tensor running_var, double eps,
+                    at::Tensor coeffs) {
+  need(gamma, at::kFloat, "gamma"); need(beta, at::kFloat, "beta"); need(running_mean, at::kFloat, "running_mean");
+  need(running_var, at::kFloat, "running_var"); need(coeffs, at::kFloat, "coeffs");
+  const int c = (int)gamma.numel();
+  TORCH_CHECK(coeffs.numel() >= 4 * c);
+  c10::cuda::CUDAGuard g(gamma.device());
+  float* co = coeffs.data_ptr<float>();
+  ddpt::launch_bn_eval_coeffs(gamma.data_ptr<float>(), beta.data_ptr<float>(), running_mean.data_ptr<float>(),
+                              running_var.data_ptr<float>(), (float)eps, c, co, co + c, cur());
+}
+
+void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bool flatten_chw) {
+  need(y, at::kBFloat16, "y"); need(coeffs, at::kFloat, "coeffs"); need(out, at::kBFloat16, "out");
+  TORCH_CHECK(y.dim() == 4);
+  const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
+  TORCH_CHECK(out.numel() == (pool ? y.numel() / 4 : y.numel()));
+  c10::cuda::CUDAGuard g(y.device());
+  const float* co = coeffs.data_ptr<float>();
+  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, cur());
+}
+
+int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor partials, bool pool, bool flatten_chw) {
+  need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
+  need(partials, at::kFloat, "partials");
+  const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
+  TORCH_CHECK(g_in.numel() == (pool ? y.numel() / 4 : y.numel()));
+  TORCH_CHECK(partials.numel() >= (int64_t)ddpt::bn_bwd_partial_rows() * 2 * c);
+  c10::cuda::CUDAGuard guard(y.device());
+  const float* co = coeffs.data_ptr<float>();
+  return ddpt::launch_bn_bwd_reduce(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, partials.data_ptr<float>(), n,
+                                    h, w, c, pool, flatten_chw, cur());
+}
+
+void bn_bwd_finalize(at::Tensor partials, int64_t num_partials, double count, at::Tensor gamma, at::Tensor coeffs,
+                     at::Tensor dgamma, at::Tensor dbeta, at::Tensor bwd_coef, bool accumulate) {
+  need(partials, at::kFloat, "partials"); need(gamma, at::kFloat, "gamma"); need(coeffs, at::kFloat, "coeffs");
+  need(dgamma, at::kFloat, "dgamma"); need(dbeta, at::kFloat, "dbeta"); need(bwd_coef, at::kFloat, "bwd_coef");
+  const int c = (int)gamma.numel();
+  TORCH_CHECK(bwd_coef.numel() >= 3 * c && dgamma.numel() == c && dbeta.numel() == c);
+  c10::cuda::CUDAGuard guard(gamma.device());
+  ddpt::launch_bn_bwd_finalize(partials.data_ptr<float>(), (int)num_partials, c, count, gamma.data_ptr<float>(),
+                               coeffs.data_ptr<float>() + 3 * c, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                               bwd_coef.data_ptr<float>(), accumulate, cur());
+}
+
+void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor bwd_coef, at::Tensor dy,
+                  c10::optional<at::Tensor> dbias, bool pool, bool flatten_chw) {
+  need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
+  need(bwd_coef, at::kFloat, "bwd_coef"); need(dy, at::kBFloat16, "dy");
+  const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
+  TORCH_CHECK(dy.numel() == y.numel());
+  c10::cuda::CUDAGuard guard(y.device());
+  const float* co = coeffs.data_ptr<float>();
+  float* db = nullptr;
+  if (dbias.has_value()) { need(*dbias, at::kFloat, "dbias"); TORCH_CHECK(dbias->numel() == c); db = dbias->data_ptr<float>(); }
+  ddpt::launch_bn_bwd_apply(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, bwd_coef.data_ptr<float>(), bfm(dy), db,
+                            n, h, w, c, pool, flatten_chw, cur());
+}
+
+// Forward-only when da is None.  dlogits: if given, used instead of the fused cross-entropy gradient.
+void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> target, c10::optional<at::Tensor> logits,
+          c10::optional<at::Tensor> metrics, c10::optional<at::Tensor> loss_scale, c10::optional<at::Tensor> da,
+          c10::optional<at::Tensor> dw, c10::optional<at::Tensor> db, c10::optional<at::Tensor> dlogits,
+          double extra_div) {
+  need(a, at::kBFloat16, "a"); need(w, at::kFloat, "w"); need(b, at::kFloat, "b");
+  TORCH_CHECK(a.dim() == 2 && a.size(1) == 512 && w.numel() == 5120 && b.numel() == 10);
+  c10::cuda::CUDAGuard guard(a.device());
+  ddpt::HeadArgs h{};
+  h.a = bf(a); h.w = w.data_ptr<float>(); h.b = b.data_ptr<float>(); h.batch = (int)a.size(0);
+  if (target.has_value()) { TORCH_CHECK(target->scalar_type() == at::kLong && target->numel() == h.batch);
+    h.target = reinterpret_cast<const long long*>(target->data_ptr<int64_t>()); }
+  if (logits.has_value()) { need(*logits, at::kFloat, "logits"); h.logits = logits->data_ptr<float>(); }
+  if (metrics.has_value()) { need(*metrics, at::kFloat, "metrics"); h.metrics = metrics->data_ptr<float>(); }
+  if (loss_scale.has_value()) h.loss_scale = loss_scale->data_ptr<float>();
+  if (da.has_value()) {
+    TORCH_CHECK(dw.has_value() && db.has_value());
+    need(*da, at::kBFloat16, "da"); need(*dw, at::kFloat, "dw"); need(*db, at::kFloat, "db");
+    h.da = bfm(*da); h.dw = dw->data_ptr<float>(); h.db = db->data_ptr<float>();
+  }
+  if (dlogits.has_value()) { need(*dlogits, at::kFloat, "dlogits"); h.dlogits = dlogits->data_ptr<float>(); }
+  TORCH_CHECK(h.target != nullptr || (h.metrics == nullptr && (h.da == nullptr || h.dlogits != nullptr)),
+              "head: target is required for metrics / fused cross-entropy gradient");
+  h.extra_div = (float)extra_div;
+  ddpt::launch_head(h, cur());
+}
+
+}  // namespace
+
+void ddpt_bind_nn(pybind11::module_& m) {
+  m.def("conv0_partial_rows", &conv0_partial_rows);
+  m.def("bn_bwd_partial_rows", &bn_bwd_partial_rows);
+  m.def("conv0_fwd", &conv0_fwd);
+  m.def("conv0_wgrad", &conv0_wgrad);
+  m.def("bn_finalize", &bn_finalize);
+  m.def("bn_eval_coeffs", &bn_eval_coeffs);
+  m.def("bn_relu_pool", &bn_relu_pool);
+  m.def("bn_bwd_reduce", &bn_bwd_reduce);
+  m.def("bn_bwd_finalize", &bn_bwd_finalize);
+  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("head", &head);
+}

@@ -1,0 +1,61 @@
+// Tensor-core GEMM / convolution kernels (tcgen05 + TMEM + TMA) -- host API.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ddpt {
+
+// One description covers: 3x3 "valid" convolution forward, its data-gradient (transposed taps,
+// zero-filled halo), and plain GEMM / linear layers (1x1 taps, W = rows, H = N = 1).
+//
+//   D[m, n] = sum_{tap, c}  A[pixel(m) + sign * tap, c] * B[n, tap, c]
+//
+// A is an NHWC bf16 tensor addressed through a 4-D TMA map (C, W, H, N); an M tile is a
+// (box_n x box_h x box_w) brick of output pixels, so every filter tap of the implicit GEMM is the
+// same TMA box shifted by (dh, dw) -- no im2col buffer and no gather.  B is a 2-D bf16 matrix:
+//   b_mn_major == 0:  [n_total, taps * C]  (row = output column n, K contiguous)       -> forward / linear
+//   b_mn_major == 1:  [C_k,     taps * n_total] (row = reduction channel, n contiguous) -> data gradient
+struct ConvGemmProblem {
+  // A operand (activations)
+  const __nv_bfloat16* a;
+  int a_c, a_w, a_h, a_n;                  // extents of the NHWC tensor (C innermost)
+  // output pixel grid and its tiling into bricks (box_w * box_h * box_n <= 128 rows per tile)
+  int out_w, out_h, out_n;
+  int box_w, box_h, box_n;
+  // filter taps: tap (r, s) reads A at (h + a_h_off + sign * r, w + a_w_off + sign * s)
+  int taps_h, taps_w, tap_sign, a_h_off, a_w_off;
+  // B operand
+  const __nv_bfloat16* b;
+  int n_total;                             // GEMM N (multiple of 64)
+  int b_mn_major;
+  long long b_ld;                          // leading dimension of B in elements
+  // epilogue
+  void* out;                               // bf16 or fp32, row-major [out_n*out_h*out_w, ld_out]
+  long long ld_out;
+  int out_fp32;                            // 1: fp32 output (atomicAdd when split_k > 1)
+  const float* bias;                       // optional, per output column
+  int relu;
+  float* stat_partials;                    // optional [num_m_tiles][2][n_total]: per-tile column sum / sum of squares
+  int split_k;                             // K splits (fp32 output only)
+};
+
+// block_n in {64, 128, 256}; returns the number of M tiles launched.
+int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
+
+// Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,
+// reduction over the pixel bricks; fp32 accumulate into a zero-initialised or beta=1 output).
+struct WgradProblem {
+  const __nv_bfloat16* dy;                 // [N, Ho, Wo, M] bf16
+  int m_total, out_w, out_h, out_n;        // M = output channels (multiple of 128 or 64)
+  const __nv_bfloat16* x;                  // [N, H, W, C] bf16
+  int c_total, in_w, in_h;                 // C = input channels (GEMM N, multiple of 64)
+  int taps_h, taps_w;
+  int box_w, box_h, box_n;                 // reduction brick (multiple of 16 pixels, <= 128)
+  float* dw;                               // [M, taps_h, taps_w, C] fp32
+  int split_k;                             // number of pixel-brick partitions (vector red.add when > 1)
+  int accumulate;                          // 1: add into dw even when split_k == 1 (beta = 1)
+};
+void launch_wgrad_gemm(const WgradProblem& p, int block_n, cudaStream_t stream);
+
+}  // namespace ddpt

@@ -1,0 +1,79 @@
+// Bandwidth-bound kernels of the fused Toy_Net pipeline (NHWC bf16) -- host API.
+// BatchNorm statistics flow as "partials": float [P][2][C] (row 0: sums, row 1: sums of squares
+// or sums of dz*xhat), produced by conv epilogues / reduce kernels and folded by *_finalize.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ddpt {
+
+// ---- conv.0 : 1 -> 64 channels, 3x3, CUDA cores (K = 9 is hostile to tensor cores) -------------
+// x: uint8 [B,28,28] (scaled by 1/255 on the fly) or fp32 [B,28,28];  y: bf16 [B,26,26,64]
+// Returns the number of statistic partial rows written ([rows][2][64]); capacity needed: conv0_partial_rows().
+int conv0_partial_rows();
+int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/, const float* bias,
+                     __nv_bfloat16* y, float* stat_partials /*[rows][2][64] or null*/, int batch, cudaStream_t s);
+// dW [64][9], db [64] accumulated with atomics into zero-initialised (or beta=1) fp32 buffers.
+void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
+                        cudaStream_t s);
+
+// ---- BatchNorm (training) ---------------------------------------------------------------------------
+struct BnCoeffs {          // all float [C]
+  float* scale;            // gamma * invstd
+  float* shift;            // beta - mean * scale
+  float* mean;
+  float* invstd;
+};
+// Fold partials into batch statistics, produce scale/shift, update running stats (momentum, unbiased var)
+// and num_batches_tracked (int64).
+void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
+                        const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
+                        float* running_var, long long* num_batches_tracked, cudaStream_t s);
+// Eval mode: scale/shift from the running statistics.
+void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float eps, int channels, float* scale, float* shift,
+                           cudaStream_t s);
+// a = relu(y * scale + shift), optionally followed by 2x2 max-pool; flatten_chw: write the pooled map
+// as [N][C*PH*PW] in (c, h, w) order -- torch's Flatten of an NCHW tensor -- for the first Linear.
+void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
+                         int h, int w, int c, int pool, int flatten_chw, cudaStream_t s);
+
+// ---- BatchNorm backward (two passes) ----------------------------------------------------------------------
+// Pass 1: partials[blk][0][c] = sum dz, partials[blk][1][c] = sum dz * xhat, with dz = grad of the BN output
+// after routing g through max-pool (if any) and the ReLU mask.  Returns the number of partial rows.
+int bn_bwd_partial_rows();
+int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, float* partials, int n, int h, int w, int c,
+                         int pool, int g_flatten_chw, cudaStream_t s);
+// Fold pass-1 partials: dgamma = sum dz*xhat, dbeta = sum dz (written/accumulated into the grad arena) and the
+// three per-channel coefficients of pass 2.
+void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
+                            const float* invstd, float* dgamma, float* dbeta, float* coef /*[3][C]*/,
+                            int accumulate, cudaStream_t s);
+// Pass 2: dy = c1 * (dz - c2 - xhat * c3) as bf16 NHWC; optionally sum dy per channel (conv bias gradient).
+void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy,
+                         float* dbias /*[C] atomics or null*/, int n, int h, int w, int c, int pool,
+                         int g_flatten_chw, cudaStream_t s);
+
+// ---- classifier head: Linear(512,10) + CrossEntropy(mean)/B + argmax, forward and backward ------------------
+struct HeadArgs {
+  const __nv_bfloat16* a;      // [B,512] relu(bn(y4))
+  const float* w;              // [10,512] fp32 master weights
+  const float* b;              // [10]
+  const long long* target;     // [B]
+  int batch;
+  float* logits;               // [B,10] fp32 (also what the caller returns as model output)
+  float* metrics;              // [2]: += sum_i CE_i / B   and  += #correct
+  // training only (null in eval)
+  const float* loss_scale;     // device scalar (amp) or null => 1
+  __nv_bfloat16* da;           // [B,512] grad wrt a (before the ReLU mask)
+  float* dw;                   // [10,512] += dlogits^T a
+  float* db;                   // [10]     += sum dlogits
+  const float* dlogits;        // optional [B,10]: externally supplied d(loss)/d(logits) (autograd path)
+  float extra_div;             // Q1: additional division of the loss by B (1/B) -> pass (float)B, or 1
+};
+void launch_head(const HeadArgs& args, cudaStream_t s);
+
+}  // namespace ddpt

@@ -1,0 +1,697 @@
+// Bandwidth-bound half of the fused Toy_Net step on sm_100a: first convolution (K = 9), BatchNorm
+// statistics / normalise / ReLU / max-pool forward and backward, and the classifier head.
+//
+// Replaces, per training step, the cuDNN BatchNorm fwd/bwd, ATen relu_/max_pool2d(+backward),
+// flatten, log_softmax/nll_loss/argmax/eq/sum kernels of the reference stack (SURVEY.md N11, N12,
+// N14; Toy_Net ops K1, K2, K4, K5, K7, K9, K10, K12-K14) with a handful of fused passes:
+//
+//   forward : conv epilogue -> stat partials -> bn_finalize -> bn_relu_pool   (1 read + <=1 write)
+//   backward: bn_bwd_reduce (1 read of y and g) -> bn_bwd_finalize -> bn_bwd_apply (1 read, 1 write)
+//
+// All activations are NHWC bf16; every thread moves 16-byte vectors (8 channels) and keeps to a
+// fixed channel group so per-channel reductions stay in registers until one block-level fold.
+#include "../include/ddpt_toynet.h"
+#include "../include/ddpt_common.cuh"
+#include <stdexcept>
+
+namespace ddpt {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+int persistent_grid(long long work_items, int per_block, int blocks_per_sm) {
+  long long want = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)sm_count() * blocks_per_sm;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ================================================================================================
+// conv.0 : direct 3x3, C_in = 1, C_out = 64
+// ================================================================================================
+constexpr int kImg = 28, kOut0 = 26, kPix0 = kOut0 * kOut0, kC0 = 64;
+
+__device__ __forceinline__ void load_image(const void* x, int x_is_u8, int img, float* s_img) {
+  if (x_is_u8) {
+    const uint8_t* src = static_cast<const uint8_t*>(x) + (size_t)img * kImg * kImg;
+    for (int i = threadIdx.x; i < kImg * kImg / 4; i += kThreads) {
+      uchar4 v = reinterpret_cast<const uchar4*>(src)[i];
+      s_img[4 * i] = v.x * (1.0f / 255.0f);
+      s_img[4 * i + 1] = v.y * (1.0f / 255.0f);
+      s_img[4 * i + 2] = v.z * (1.0f / 255.0f);
+      s_img[4 * i + 3] = v.w * (1.0f / 255.0f);
+    }
+  } else {
+    const float* src = static_cast<const float*>(x) + (size_t)img * kImg * kImg;
+    for (int i = threadIdx.x; i < kImg * kImg; i += kThreads) s_img[i] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restrict__ weight,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ partials,
+                 int batch) {
+  __shared__ float s_img[kImg * kImg];
+  __shared__ float s_red[2][kC0];
+  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  float wr[8][9], br[8], acc_s[8], acc_q[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias[cg * 8 + c];
+    acc_s[c] = acc_q[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = weight[(cg * 8 + c) * 9 + t];
+  }
+  for (int img = blockIdx.x; img < batch; img += gridDim.x) {
+    __syncthreads();
+    load_image(x, x_is_u8, img, s_img);
+    __syncthreads();
+    for (int p = prow; p < kPix0; p += kThreads / 8) {
+      const int oh = p / kOut0, ow = p - oh * kOut0;
+      float in[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) in[r * 3 + q] = s_img[(oh + r) * kImg + ow + q];
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = br[c];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v = fmaf(wr[c][t], in[t], v);
+        o[c] = v;
+        acc_s[c] += v;
+        acc_q[c] = fmaf(v, v, acc_q[c]);
+      }
+      *reinterpret_cast<uint4*>(y + ((size_t)img * kPix0 + p) * kC0 + cg * 8) = pack8(o);
+    }
+  }
+  if (partials == nullptr) return;
+  // fold the 32 threads sharing a channel group: 4 lanes per warp (xor 8, 16), then 8 warps via smem
+  if (threadIdx.x < 2 * kC0) (&s_red[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float s = acc_s[c], q = acc_q[c];
+    s += __shfl_xor_sync(0xffffffffu, s, 8);  q += __shfl_xor_sync(0xffffffffu, q, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
+    if ((threadIdx.x & 31) < 8) {
+      atomicAdd(&s_red[0][cg * 8 + c], s);
+      atomicAdd(&s_red[1][cg * 8 + c], q);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kC0) partials[(size_t)blockIdx.x * 2 * kC0 + threadIdx.x] = (&s_red[0][0])[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16* __restrict__ dy,
+                   float* __restrict__ dw, float* __restrict__ db, int batch) {
+  __shared__ float s_img[kImg * kImg];
+  __shared__ float s_acc[kC0 * 10];
+  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  float acc[8][10];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[c][t] = 0.f;
+  for (int img = blockIdx.x; img < batch; img += gridDim.x) {
+    __syncthreads();
+    load_image(x, x_is_u8, img, s_img);
+    __syncthreads();
+    for (int p = prow; p < kPix0; p += kThreads / 8) {
+      const int oh = p / kOut0, ow = p - oh * kOut0;
+      float g[8];
+      unpack8(ldg16(dy + ((size_t)img * kPix0 + p) * kC0 + cg * 8), g);
+      float in[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) in[r * 3 + q] = s_img[(oh + r) * kImg + ow + q];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+        acc[c][9] += g[c];
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < kC0 * 10; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      float v = acc[c][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(cg * 8 + c) * 10 + t], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC0 * 10; i += kThreads) {
+    const int ch = i / 10, t = i - ch * 10;
+    if (t < 9) atomicAdd(dw + ch * 9 + t, s_acc[i]);
+    else atomicAdd(db + ch, s_acc[i]);
+  }
+}
+
+// ================================================================================================
+// BatchNorm forward
+// ================================================================================================
+// One block per 32 channels; 8 row-groups of 32 lanes walk the partial rows (coalesced across channels).
+__global__ void __launch_bounds__(kThreads)
+bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   BnCoeffs out, float* __restrict__ running_mean, float* __restrict__ running_var,
+                   long long* __restrict__ nbt) {
+  __shared__ double s_sum[8][32], s_sq[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double sum = 0.0, sq = 0.0;
+  if (c < channels) {
+    for (int p = grp; p < num_partials; p += 8) {
+      sum += (double)partials[((size_t)p * 2) * channels + c];
+      sq += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    }
+  }
+  s_sum[grp][lane] = sum;
+  s_sq[grp][lane] = sq;
+  __syncthreads();
+  if (grp == 0 && c < channels) {
+    for (int g = 1; g < 8; ++g) { sum += s_sum[g][lane]; sq += s_sq[g][lane]; }
+    const double mean = sum / count;
+    double var = sq / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    out.scale[c] = sc;
+    out.shift[c] = beta[c] - (float)mean * sc;
+    out.mean[c] = (float)mean;
+    out.invstd[c] = invstd;
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      int channels, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+// a = relu(y*scale+shift) [+ 2x2 max-pool]; one thread = one output pixel x 8 channels.
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads)
+bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c) {
+  const int cv = c >> 3;
+  const int oh = POOL ? h >> 1 : h, ow = POOL ? w >> 1 : w;
+  const long long total = (long long)n * oh * ow * cv;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int v = (int)(i % cv);
+    const long long pix = i / cv;
+    float sc[8], sh[8];
+    load8f(scale + v * 8, sc);
+    load8f(shift + v * 8, sh);
+    float r[8];
+    if (!POOL) {
+      float f[8];
+      unpack8(ldg16(y + pix * c + v * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+    } else {
+      const int pw = (int)(pix % ow);
+      const int ph = (int)((pix / ow) % oh);
+      const long long img = pix / ((long long)ow * oh);
+      const __nv_bfloat16* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = 0.f;            // relu floor
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack8(ldg16(base + ((q >> 1) * w + (q & 1)) * c), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaxf(r[k], fmaf(f[k], sc[k], sh[k]));
+      }
+    }
+    *reinterpret_cast<uint4*>(out + pix * c + v * 8) = pack8(r);
+  }
+}
+
+// Pooled + flattened in (c, ph, pw) order for the first Linear: one block per image, smem transpose.
+__global__ void __launch_bounds__(kThreads)
+bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c) {
+  extern __shared__ __nv_bfloat16 s_t[];                  // [c][ppix + 2] (padded)
+  const int oh = h >> 1, ow = w >> 1, ppix = oh * ow, cv = c >> 3, ld = ppix + 2;
+  const long long img = blockIdx.x;
+  for (int i = threadIdx.x; i < ppix * cv; i += kThreads) {
+    const int v = i % cv, pp = i / cv;
+    const int ph = pp / ow, pw = pp - ph * ow;
+    float sc[8], sh[8], r[8];
+    load8f(scale + v * 8, sc);
+    load8f(shift + v * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = 0.f;
+    const __nv_bfloat16* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+      unpack8(ldg16(base + ((q >> 1) * w + (q & 1)) * c), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = fmaxf(r[k], fmaf(f[k], sc[k], sh[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_t[(v * 8 + k) * ld + pp] = __float2bfloat16(r[k]);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + img * (long long)c * ppix;
+  for (int i = threadIdx.x; i < c * ppix; i += kThreads) dst[i] = s_t[(i / ppix) * ld + (i % ppix)];
+}
+
+// ================================================================================================
+// BatchNorm backward
+// ================================================================================================
+// dz for one 8-channel vector of one (pooled) output position; also returns xhat at the routed position(s).
+struct BwdCtx {
+  const __nv_bfloat16* y; const __nv_bfloat16* g;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  int n, h, w, c, flatten;
+};
+
+__device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, int pw, int oh, int ow, int v,
+                                       float (&g)[8]) {
+  if (!k.flatten) {
+    unpack8(ldg16(k.g + ((img * oh + ph) * ow + pw) * k.c + v * 8), g);
+  } else {
+    const __nv_bfloat16* base = k.g + img * (long long)k.c * oh * ow + (long long)(v * 8) * oh * ow + ph * ow + pw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = __bfloat162float(base[(long long)j * oh * ow]);
+  }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
+  extern __shared__ float s_part[];                       // [2][c]
+  const int cv = k.c >> 3;
+  const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
+  const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
+  const long long total_pix = (long long)k.n * oh * ow;
+  float sc[8], sh[8], mu[8], is[8], s_dz[8], s_dzx[8];
+  load8f(k.scale + v * 8, sc); load8f(k.shift + v * 8, sh);
+  load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_dz[j] = s_dzx[j] = 0.f;
+  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix;
+       pix += (long long)gridDim.x * rows_per_blk) {
+    const int pw = (int)(pix % ow);
+    const int ph = (int)((pix / ow) % oh);
+    const long long img = pix / ((long long)ow * oh);
+    float g[8];
+    load_g(k, img, ph, pw, oh, ow, v, g);
+    if (!POOL) {
+      float f[8];
+      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float dz = z > 0.f ? g[j] : 0.f;
+        s_dz[j] += dz;
+        s_dzx[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s_dzx[j]);
+      }
+    } else {
+      const __nv_bfloat16* base = k.y + ((img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
+      float best[8], besty[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }     // z <= 0 everywhere -> no gradient
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack8(ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dz = best[j] > 0.f ? g[j] : 0.f;
+        s_dz[j] += dz;
+        s_dzx[j] = fmaf(dz, (besty[j] - mu[j]) * is[j], s_dzx[j]);
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) s_part[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_part[v * 8 + j], s_dz[j]);
+    atomicAdd(&s_part[k.c + v * 8 + j], s_dzx[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) partials[(size_t)blockIdx.x * 2 * k.c + i] = s_part[i];
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
+                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                       int accumulate) {
+  __shared__ double s_a[8][32], s_b[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a = 0.0, b = 0.0;
+  if (c < channels) {
+    for (int p = grp; p < num_partials; p += 8) {
+      a += (double)partials[((size_t)p * 2) * channels + c];
+      b += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    }
+  }
+  s_a[grp][lane] = a;
+  s_b[grp][lane] = b;
+  __syncthreads();
+  if (grp == 0 && c < channels) {
+    for (int g = 1; g < 8; ++g) { a += s_a[g][lane]; b += s_b[g][lane]; }
+    if (accumulate) { dbeta[c] += (float)a; dgamma[c] += (float)b; }
+    else { dbeta[c] = (float)a; dgamma[c] = (float)b; }
+    coef[c] = gamma[c] * invstd[c];
+    coef[channels + c] = (float)(a / count);
+    coef[2 * channels + c] = (float)(b / count);
+  }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
+                    float* __restrict__ dbias) {
+  extern __shared__ float s_db[];                          // [c]
+  const int cv = k.c >> 3;
+  const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
+  const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
+  const long long total_pix = (long long)k.n * oh * ow;
+  float sc[8], sh[8], mu[8], is[8], c1[8], c2[8], c3[8], db[8];
+  load8f(k.scale + v * 8, sc); load8f(k.shift + v * 8, sh);
+  load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
+  load8f(coef + v * 8, c1); load8f(coef + k.c + v * 8, c2); load8f(coef + 2 * k.c + v * 8, c3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) db[j] = 0.f;
+  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix;
+       pix += (long long)gridDim.x * rows_per_blk) {
+    const int pw = (int)(pix % ow);
+    const int ph = (int)((pix / ow) % oh);
+    const long long img = pix / ((long long)ow * oh);
+    float g[8];
+    load_g(k, img, ph, pw, oh, ow, v, g);
+    if (!POOL) {
+      float f[8], o[8];
+      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float dz = z > 0.f ? g[j] : 0.f;
+        o[j] = c1[j] * (dz - c2[j] - (f[j] - mu[j]) * is[j] * c3[j]);
+        db[j] += o[j];
+      }
+      *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
+    } else {
+      const long long base_off = ((img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
+      float f[4][8];
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unpack8(ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c), f[q]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[q][j], sc[j], sh[j]);
+          if (z > best[j]) { best[j] = z; arg[j] = q; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dz = arg[j] == q ? g[j] : 0.f;
+          o[j] = c1[j] * (dz - c2[j] - (f[q][j] - mu[j]) * is[j] * c3[j]);
+          db[j] += o[j];
+        }
+        *reinterpret_cast<uint4*>(dy + base_off + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
+      }
+    }
+  }
+  if (dbias == nullptr) return;
+  for (int i = threadIdx.x; i < k.c; i += kThreads) s_db[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_db[v * 8 + j], db[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < k.c; i += kThreads) atomicAdd(dbias + i, s_db[i]);
+}
+
+// ================================================================================================
+// Head: Linear(512,10) + CE(mean)/B + argmax (+ backward)
+// ================================================================================================
+constexpr int kFeat = 512, kCls = 10, kHeadRows = 8;   // one warp per row, 8 rows per block iteration
+
+__global__ void __launch_bounds__(kThreads)
+head_kernel(HeadArgs a) {
+  __shared__ float s_w[kCls][kFeat];
+  __shared__ float s_dw[kCls][kFeat];
+  __shared__ float s_db[kCls];
+  __shared__ float s_metric[2];
+  const bool train = a.da != nullptr;
+  for (int i = threadIdx.x; i < kCls * kFeat; i += kThreads) {
+    (&s_w[0][0])[i] = a.w[i];
+    if (train) (&s_dw[0][0])[i] = 0.f;
+  }
+  if (threadIdx.x < kCls) s_db[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2) s_metric[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_b = 1.0f / (float)a.batch;
+  const float gscale = train ? (a.loss_scale ? *a.loss_scale : 1.0f) * inv_b / a.extra_div : 0.f;
+  float my_loss = 0.f, my_correct = 0.f;
+  for (int row = blockIdx.x * kHeadRows + warp; row < a.batch; row += gridDim.x * kHeadRows) {
+    // lane owns features {64*j + 2*lane + e : j < 8, e < 2}: 4-byte coalesced loads, conflict-light smem
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(a.a + (size_t)row * kFeat + 64 * j + 2 * lane);
+      const float2 f = __bfloat1622float2(v);
+      x[2 * j] = f.x;
+      x[2 * j + 1] = f.y;
+    }
+    float logit[kCls];
+#pragma unroll
+    for (int k = 0; k < kCls; ++k) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p = fmaf(x[j], s_w[k][64 * (j >> 1) + 2 * lane + (j & 1)], p);
+      logit[k] = warp_sum(p) + a.b[k];
+    }
+    float mx = logit[0];
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < kCls; ++k) if (logit[k] > mx) { mx = logit[k]; arg = k; }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCls; ++k) den += __expf(logit[k] - mx);
+    const int tgt = a.target != nullptr ? (int)a.target[row] : -1;
+    float tl = logit[0];
+#pragma unroll
+    for (int k = 1; k < kCls; ++k) tl = (k == tgt) ? logit[k] : tl;
+    if (lane == 0) {
+      if (tgt >= 0) {
+        my_loss += (mx + __logf(den)) - tl;
+        my_correct += (arg == tgt) ? 1.f : 0.f;
+      }
+      if (a.logits != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kCls; ++k) a.logits[(size_t)row * kCls + k] = logit[k];
+      }
+    }
+    if (train) {
+      float dl[kCls];
+      const float inv_den = 1.0f / den;
+#pragma unroll
+      for (int k = 0; k < kCls; ++k)
+        dl[k] = a.dlogits != nullptr ? a.dlogits[(size_t)row * kCls + k]
+                                     : (__expf(logit[k] - mx) * inv_den - (k == tgt ? 1.f : 0.f)) * gscale;
+      float dx[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dx[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kCls; ++k) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int f = 64 * (j >> 1) + 2 * lane + (j & 1);
+          dx[j] = fmaf(dl[k], s_w[k][f], dx[j]);
+          atomicAdd(&s_dw[k][f], dl[k] * x[j]);
+        }
+        if (lane == 0) atomicAdd(&s_db[k], dl[k]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint32_t*>(a.da + (size_t)row * kFeat + 64 * j + 2 * lane) = pack_bf16x2(dx[2 * j], dx[2 * j + 1]);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&s_metric[0], my_loss);
+    atomicAdd(&s_metric[1], my_correct);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && a.metrics != nullptr) {
+    atomicAdd(a.metrics, s_metric[0] * inv_b / a.extra_div * (float)a.batch);   // += batch_loss * B
+    atomicAdd(a.metrics + 1, s_metric[1]);
+  }
+  if (train) {
+    for (int i = threadIdx.x; i < kCls * kFeat; i += kThreads) atomicAdd(a.dw + i, (&s_dw[0][0])[i]);
+    if (threadIdx.x < kCls) atomicAdd(a.db + threadIdx.x, s_db[threadIdx.x]);
+  }
+}
+
+}  // namespace
+
+// ---- launchers -------------------------------------------------------------------------------------
+int conv0_partial_rows() { return sm_count() * 2; }
+
+int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const float* bias, __nv_bfloat16* y,
+                     float* stat_partials, int batch, cudaStream_t s) {
+  const int grid = batch < conv0_partial_rows() ? batch : conv0_partial_rows();
+  conv0_fwd_kernel<<<grid, kThreads, 0, s>>>(x, x_is_u8, weight, bias, y, stat_partials, batch);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+  return grid;
+}
+
+void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
+                        cudaStream_t s) {
+  const int grid = batch < sm_count() * 2 ? batch : sm_count() * 2;
+  conv0_wgrad_kernel<<<grid, kThreads, 0, s>>>(x, x_is_u8, dy, dw, db, batch);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
+                        const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
+                        float* running_var, long long* nbt, cudaStream_t s) {
+  bn_finalize_kernel<<<(channels + 31) / 32, kThreads, 0, s>>>(partials, num_partials, channels, count, gamma, beta,
+                                                                eps, momentum, out, running_mean, running_var, nbt);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float eps, int channels, float* scale, float* shift,
+                           cudaStream_t s) {
+  bn_eval_coeffs_kernel<<<(channels + 127) / 128, 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, channels,
+                                                               scale, shift);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+static void check_channels(int c) {
+  if (c % 8 != 0 || kThreads % (c / 8) != 0 || c > 2048)
+    throw std::runtime_error("toynet elementwise kernels need C % 8 == 0 and (C/8) dividing 256");
+}
+
+void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
+                         int h, int w, int c, int pool, int flatten_chw, cudaStream_t s) {
+  check_channels(c);
+  if (pool && ((h | w) & 1)) throw std::runtime_error("2x2 max-pool needs even H and W");
+  if (flatten_chw) {
+    if (!pool) throw std::runtime_error("flatten_chw is only implemented together with the pool");
+    const int ppix = (h / 2) * (w / 2);
+    const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
+    bn_relu_pool_flatten_kernel<<<n, kThreads, smem, s>>>(y, scale, shift, out, h, w, c);
+  } else {
+    const long long total = (long long)n * (pool ? (h / 2) * (w / 2) : h * w) * (c / 8);
+    const int grid = persistent_grid(total, kThreads, 16);
+    if (pool) bn_relu_pool_kernel<true><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
+    else bn_relu_pool_kernel<false><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
+  }
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+int bn_bwd_partial_rows() { return sm_count() * 4; }
+
+int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, float* partials, int n, int h, int w, int c,
+                         int pool, int g_flatten_chw, cudaStream_t s) {
+  check_channels(c);
+  BwdCtx k{y, g, scale, shift, mean, invstd, n, h, w, c, g_flatten_chw};
+  const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
+  const int rows_per_blk = kThreads / (c / 8);
+  long long want = (pix + rows_per_blk - 1) / rows_per_blk;
+  const int grid = (int)(want < bn_bwd_partial_rows() ? want : bn_bwd_partial_rows());
+  const size_t smem = 2 * c * sizeof(float);
+  if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(k, partials);
+  else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(k, partials);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+  return grid;
+}
+
+void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
+                            const float* invstd, float* dgamma, float* dbeta, float* coef, int accumulate,
+                            cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<(channels + 31) / 32, kThreads, 0, s>>>(partials, num_partials, channels, count, gamma,
+                                                                    invstd, dgamma, dbeta, coef, accumulate);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy, float* dbias,
+                         int n, int h, int w, int c, int pool, int g_flatten_chw, cudaStream_t s) {
+  check_channels(c);
+  BwdCtx k{y, g, scale, shift, mean, invstd, n, h, w, c, g_flatten_chw};
+  const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
+  const int rows_per_blk = kThreads / (c / 8);
+  long long want = (pix + rows_per_blk - 1) / rows_per_blk;
+  const int cap = sm_count() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  const size_t smem = c * sizeof(float);
+  if (pool) bn_bwd_apply_kernel<true><<<grid, kThreads, smem, s>>>(k, coef, dy, dbias);
+  else bn_bwd_apply_kernel<false><<<grid, kThreads, smem, s>>>(k, coef, dy, dbias);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_head(const HeadArgs& args, cudaStream_t s) {
+  int grid = (args.batch + kHeadRows - 1) / kHeadRows;
+  const int cap = sm_count();
+  if (grid > cap) grid = cap;
+  head_kernel<<<grid, kThreads, 0, s>>>(args);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ddpt

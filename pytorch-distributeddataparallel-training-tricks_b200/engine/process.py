@@ -54,6 +54,17 @@ def iterate_loader(loader, model: torch.nn.Module, loss_function, local_rank: in
         progress = not getattr(loader, "quiet", False)
     engine = getattr(model, "_ddpt_step_engine", None) if device.type == "cuda" else None
 
+    if engine is not None and engine.accepts(model, loss_function, apex_optimizer, training):
+        # fused path: one CUDA-graph replay per batch, metrics stay on the device until the end of the pass
+        engine.begin_pass()
+        for image, target in _progress(loader, progress):
+            engine.run(image, target, training)
+        loss_total, correct_total, seen = engine.end_pass()
+        mean_loss, accuracy = loss_total / max(seen, 1), correct_total / max(seen, 1)
+        if training:
+            return mean_loss, accuracy, apex_optimizer.param_groups[0]["lr"]
+        return mean_loss, accuracy
+
     loss_sum = torch.zeros((), dtype=torch.float64 if device.type == "cpu" else torch.float32, device=device)
     correct = torch.zeros((), dtype=torch.int64, device=device)
     seen = 0
@@ -64,11 +75,6 @@ def iterate_loader(loader, model: torch.nn.Module, loss_function, local_rank: in
         if target.device != device or target.dtype != torch.long:
             target = target.to(device, dtype=torch.long, non_blocking=True)
         batch = image.shape[0]
-
-        if engine is not None and engine.accepts(model, loss_function, apex_optimizer, training):
-            engine.run(image, target, training, loss_sum, correct)
-            seen += batch
-            continue
 
         if training:
             apex_optimizer.zero_grad()

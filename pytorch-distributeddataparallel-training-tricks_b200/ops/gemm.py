@@ -1,0 +1,128 @@
+"""Tensor-core convolution / linear primitives (tcgen05 + TMEM + TMA), NHWC bf16.
+
+Thin wrappers over ``_ddpt_C.conv_gemm`` / ``_ddpt_C.wgrad_gemm`` that pick the output brick
+(the M tile is a box of output pixels, see csrc/nn/conv_gemm.cu) and the N tile.  Layout
+conventions used throughout the fused Toy_Net path:
+
+* activations: ``[N, H, W, C]`` bf16 contiguous;
+* conv weights: ``[C_out, kh*kw*C_in]`` bf16 -- the channels-last physical order of the fp32
+  master weights in the parameter arena, so the bf16 shadow is a plain element-wise cast;
+* weight gradients: fp32 ``[C_out, kh, kw, C_in]`` -- again the arena's physical order.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Optional, Tuple
+
+import torch
+
+from . import require_native
+
+
+@functools.lru_cache(maxsize=None)
+def pick_box(out_n: int, out_h: int, out_w: int, multiple_of: int = 1, max_rows: int = 128) -> Tuple[int, int, int]:
+    """Brick (bn, bh, bw) of output pixels with bn*bh*bw <= 128 that wastes the fewest MMA rows."""
+    best, best_key = None, None
+    total = out_n * out_h * out_w
+    for bw in range(1, min(out_w, max_rows) + 1):
+        for bh in range(1, min(out_h, max_rows // bw) + 1):
+            bn = min(out_n, max_rows // (bw * bh))
+            while bn >= 1:
+                rows = bw * bh * bn
+                if rows % multiple_of == 0:
+                    tiles = -(-out_w // bw) * -(-out_h // bh) * -(-out_n // bn)
+                    eff = total / (tiles * (max_rows if multiple_of == 1 else rows))
+                    key = (round(eff, 4), bw, bh)
+                    if best_key is None or key > best_key:
+                        best, best_key = (bn, bh, bw), key
+                    break
+                bn -= 1
+    if best is None:
+        raise ValueError(f"no brick for output {out_n}x{out_h}x{out_w}")
+    return best
+
+
+def _block_n(n_total: int, prefer: Optional[int]) -> int:
+    if prefer is not None:
+        return prefer
+    for bn in (256, 128, 64):
+        if n_total % bn == 0:
+            return bn
+    raise ValueError(f"N={n_total} is not a multiple of 64")
+
+
+def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
+             relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1):
+    """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
+    ext = require_native()
+    n, h, w, c = x.shape
+    ho, wo = h - kh + 1, w - kw + 1
+    c_out = w_km.shape[0]
+    if out is None:
+        out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
+    box = pick_box(n, ho, wo)
+    tiles = ext.conv_gemm(x, w_km, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], 1, [0, 0], False,
+                          bias, relu, stat_partials, split_k, _block_n(c_out, block_n))
+    return out, tiles
+
+
+def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
+               block_n: Optional[int] = None):
+    """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
+    ext = require_native()
+    n, ho, wo, c_out = dy.shape
+    h, w = ho + kh - 1, wo + kw - 1
+    c_in = w_km.shape[1] // (kh * kw)
+    if out is None:
+        out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
+    box = pick_box(n, h, w)
+    ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
+                  None, False, None, 1, _block_n(c_in, block_n))
+    return out
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
+               split_k: Optional[int] = None, accumulate: bool = False, block_n: Optional[int] = None):
+    """dW [C_out, kh, kw, C_in] fp32 = sum over pixels dy[p, :]^T x[p + tap, :]."""
+    ext = require_native()
+    n, ho, wo, c_out = dy.shape
+    c_in = x.shape[3]
+    box = pick_box(n, ho, wo, 16)
+    bn = _block_n(c_in, block_n)
+    if split_k is None:
+        bricks = -(-wo // box[2]) * -(-ho // box[1]) * -(-n // box[0])
+        ctas = (c_out // 128) * kh * kw * (c_in // bn)
+        sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
+        split_k = max(1, min(bricks, -(-2 * sms // ctas)))
+    if out is None:
+        out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
+    elif split_k > 1 and not accumulate:
+        out.zero_()
+    ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn)
+    return out
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+               stat_partials: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split_k: int = 1,
+               block_n: Optional[int] = None):
+    """y [M, N] = x [M, K] @ w [N, K]^T (+ bias)."""
+    m, k = x.shape
+    y, tiles = conv_fwd(x.view(1, 1, m, k), w, 1, 1, bias, relu, stat_partials, None, block_n, out_dtype, split_k)
+    return y.view(m, w.shape[0]), tiles
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None):
+    """dx [M, K] = dy [M, N] @ w [N, K]."""
+    m, n = dy.shape
+    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n).view(m, w.shape[1])
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 split_k: Optional[int] = None, accumulate: bool = False):
+    """dw [N, K] fp32 = dy [M, N]^T @ x [M, K]."""
+    m, n = dy.shape
+    k = x.shape[1]
+    res = conv_wgrad(dy.view(1, 1, m, n), x.view(1, 1, m, k), 1, 1,
+                     None if out is None else out.view(n, 1, 1, k), split_k, accumulate)
+    return res.view(n, k)

@@ -1,0 +1,261 @@
+"""Fused sm_100a forward/backward of Toy_Net (reference model: utils/model.py:4-34).
+
+Dataflow (NHWC bf16 activations, fp32 statistics / parameters / gradients)::
+
+    u8 image --conv0 (CUDA cores, K=9) + stats--> y0 --bn_finalize--> bn+relu --> a0
+    a0 --tcgen05 implicit-GEMM conv (+bias, +stat partials in the epilogue)--> y1
+       --bn_finalize--> bn+relu+maxpool --> a1 ... (x3) ... --> a3 [B, 8192] in torch's (c,h,w) order
+    a3 --tcgen05 GEMM (+bias, +stats)--> y4 --bn_finalize--> bn+relu --> a4 --head--> logits [B,10]
+
+    backward mirrors it: head -> BN1d bwd (reduce / finalize / apply) -> tcgen05 wgrad + dgrad
+    (MN-major operands, no transposes) -> BN bwd + pool/ReLU routing -> ... -> conv0 wgrad.
+
+Two entry points share the implementation:
+
+* ``model(x)`` (autograd): :class:`_ToyNetFunction` returns logits, autograd supplies d(logits);
+  parameter gradients come back through autograd so hooks / accumulation behave as usual.
+* the step engine (``ops.step_engine``) calls :meth:`FusedToyNet.forward_impl` /
+  :meth:`backward_impl` directly, with cross-entropy fused into the head kernel and parameter
+  gradients written straight into the DDP gradient arena.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import require_native
+from . import gemm
+
+_EPS, _MOMENTUM = 1e-5, 0.1
+# (param index of conv weight, H_in, C_in, C_out, pool) for the three tensor-core conv blocks
+_TC_BLOCKS = ((4, 26, 64, 128, True), (8, 12, 128, 256, False), (12, 10, 256, 512, True))
+
+
+class _Workspace:
+    """Static activation / scratch buffers for one batch size (CUDA-graph friendly)."""
+
+    def __init__(self, ext, batch: int, device):
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)
+        self.batch = batch
+        self.y = [e(batch, 26, 26, 64), e(batch, 24, 24, 128), e(batch, 10, 10, 256), e(batch, 8, 8, 512),
+                  e(batch, 1, 1, 512)]
+        self.a = [e(batch, 26, 26, 64), e(batch, 12, 12, 128), e(batch, 10, 10, 256), e(batch, 8192),
+                  e(batch, 512)]
+        self.coef = [torch.zeros(4, c, dtype=f32, device=device) for c in (64, 128, 256, 512, 512)]
+        self.bcoef = [torch.zeros(3, c, dtype=f32, device=device) for c in (64, 128, 256, 512, 512)]
+        self.logits = e(batch, 10, dt=f32)
+        # statistic partial rows: conv epilogues write 4 rows (warp quadrants) per M tile
+        def tiles(n, h, w):
+            bn_, bh, bw = gemm.pick_box(n, h, w)
+            return -(-w // bw) * -(-h // bh) * -(-n // bn_)
+        rows = [ext.conv0_partial_rows(), 4 * tiles(batch, 24, 24), 4 * tiles(batch, 10, 10),
+                4 * tiles(batch, 8, 8), 4 * tiles(1, 1, batch)]
+        chans = (64, 128, 256, 512, 512)
+        self.part = torch.zeros(max(max(r * 2 * c for r, c in zip(rows, chans)),
+                                    ext.bn_bwd_partial_rows() * 2 * 512), dtype=f32, device=device)
+        # backward
+        self.dy = [e(batch, 26, 26, 64), e(batch, 24, 24, 128), e(batch, 10, 10, 256), e(batch, 8, 8, 512),
+                   e(batch, 512)]
+        self.da = [e(batch, 26, 26, 64), e(batch, 12, 12, 128), e(batch, 10, 10, 256), e(batch, 8192),
+                   e(batch, 512)]
+        self.saved_x: Optional[torch.Tensor] = None
+
+
+class FusedToyNet:
+    def __init__(self, model, compute: str = "bf16"):
+        self.ext = require_native()
+        self.model = model
+        self.compute = compute
+        self.params: List[torch.nn.Parameter] = list(model.parameters())
+        if len(self.params) != 22:
+            raise ValueError("FusedToyNet expects the 22-parameter Toy_Net")
+        self.device = self.params[0].device
+        self.bn = [model.conv[1], model.conv[4], model.conv[8], model.conv[11], model.dense[2]]
+        self._ws: Dict[int, _Workspace] = {}
+        self._shadow_cache: Dict[int, tuple] = {}
+        self._staging: Optional[torch.Tensor] = None
+        self.launches = 0
+
+    def count_launches(self, batch: int) -> int:
+        """Kernels of ours in one training step (forward + backward + unscale + scale update + optimizer)."""
+        fwd = 1 + 1 + 1 + 3 * 3 + 3 + 1          # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio | head
+        bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
+        return fwd + bwd + 3
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def workspace(self, batch: int) -> _Workspace:
+        ws = self._ws.get(batch)
+        if ws is None:
+            ws = self._ws[batch] = _Workspace(self.ext, batch, self.device)
+        return ws
+
+    def _weight_bf16(self, pidx: int) -> torch.Tensor:
+        """bf16 [C_out, kh*kw*C_in] (channels-last physical order) or [N, K] for linear weights."""
+        p = self.params[pidx]
+        fused_opt = getattr(self.model, "_ddpt_fused_optim", None)
+        if fused_opt is not None and fused_opt.arena.channels_last:
+            return fused_opt.shadow_view(pidx).view(p.shape[0], -1)
+        key = (p.data_ptr(), p._version)
+        hit = self._shadow_cache.get(pidx)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        src = p.detach()
+        if src.dim() == 4:
+            src = src.permute(0, 2, 3, 1)
+        w = src.reshape(p.shape[0], -1).to(torch.bfloat16).contiguous()
+        self._shadow_cache[pidx] = (key, w)
+        return w
+
+    def _grad_view(self, flat: torch.Tensor, offset: int, p: torch.Tensor) -> torch.Tensor:
+        v = flat[offset: offset + p.numel()]
+        if p.dim() == 4:
+            co, ci, kh, kw = p.shape
+            return v.view(co, kh, kw, ci)            # physical order of the kernels' output
+        return v.view(p.shape)
+
+    def staging_grads(self) -> List[torch.Tensor]:
+        """Per-parameter fp32 buffers (conv weights as [C_out,kh,kw,C_in]) inside one flat allocation."""
+        if self._staging is None:
+            total, offs = 0, []
+            for p in self.params:
+                offs.append(total)
+                total += (p.numel() + 3) // 4 * 4
+            self._staging = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self._staging_views = [self._grad_view(self._staging, o, p) for o, p in zip(offs, self.params)]
+        return self._staging_views
+
+    def arena_grads(self, arena) -> List[torch.Tensor]:
+        if not arena.channels_last:
+            raise RuntimeError("fused Toy_Net writes channels-last weight gradients; arena must match")
+        return [self._grad_view(arena.grad_arena, arena.offset_of[i], p) for i, p in enumerate(self.params)]
+
+    # -- forward ---------------------------------------------------------------------------------------
+    def _bn_coeffs(self, k: int, ws: _Workspace, train: bool, rows: int, count: float) -> None:
+        bn = self.bn[k]
+        if train:
+            self.ext.bn_finalize(ws.part, rows, count, bn.weight, bn.bias, _EPS, _MOMENTUM, ws.coef[k],
+                                 bn.running_mean, bn.running_var, bn.num_batches_tracked)
+        else:
+            self.ext.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, _EPS, ws.coef[k])
+
+    def forward_impl(self, x: torch.Tensor, train: bool, target: Optional[torch.Tensor] = None,
+                     metrics: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ext, P = self.ext, self.params
+        if x.dim() == 4:
+            if x.shape[1] != 1:
+                raise ValueError("Toy_Net takes single-channel 28x28 images")
+        x = x.contiguous()
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        batch = x.numel() // 784
+        ws = self.workspace(batch)
+        ws.saved_x = x
+        part = ws.part if train else None
+        # block 0: direct conv + BN + ReLU
+        rows = ext.conv0_fwd(x, P[0].detach().reshape(64, 9).contiguous(), P[1].detach(), ws.y[0], part)
+        self._bn_coeffs(0, ws, train, rows, batch * 676.0)
+        ext.bn_relu_pool(ws.y[0], ws.coef[0], ws.a[0], False, False)
+        # blocks 1..3: tcgen05 implicit GEMM + BN + ReLU (+pool)
+        act = ws.a[0]
+        for k, (pidx, h_in, c_in, c_out, pool) in enumerate(_TC_BLOCKS, start=1):
+            h_out = h_in - 2
+            _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
+            self._bn_coeffs(k, ws, train, 4 * tiles, batch * float(h_out * h_out))
+            ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, k == 3)
+            act = ws.a[k]
+        # dense.1 + BN1d + ReLU
+        y4 = ws.y[4].view(batch, 512)
+        _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(), False,
+                                 part, y4.view(1, 1, batch, 512), block_n=64)
+        self._bn_coeffs(4, ws, train, 4 * tiles, float(batch))
+        ext.bn_relu_pool(ws.y[4], ws.coef[4], ws.a[4], False, False)
+        # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)
+        ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, ws.logits, metrics, None, None, None, None, None,
+                 float(batch))
+        return ws.logits
+
+    # -- backward --------------------------------------------------------------------------------------
+    def backward_impl(self, batch: int, grads: List[torch.Tensor], dlogits: Optional[torch.Tensor] = None,
+                      target: Optional[torch.Tensor] = None, loss_scale: Optional[torch.Tensor] = None,
+                      on_ready: Optional[Callable[[int], None]] = None) -> None:
+        """Write d(loss)/d(param) into ``grads`` (zero-initialised by the caller).
+
+        Either ``dlogits`` (autograd path) or ``target`` (fused CE with the reference's extra 1/B and the
+        device-resident ``loss_scale``) selects the loss gradient.  ``on_ready(param_index)`` fires as
+        soon as a parameter's gradient is final -- in the order DDP buckets expect."""
+        ext, P, ws = self.ext, self.params, self.workspace(batch)
+        ready = on_ready or (lambda i: None)
+        x = ws.saved_x
+        ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, None, None, loss_scale, ws.da[4], grads[20],
+                 grads[21], dlogits, float(batch))
+        ready(21); ready(20)
+        # BN1d backward -> dy4
+        self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=17)
+        ready(19); ready(18); ready(17)
+        dy4 = ws.dy[4]
+        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], accumulate=True)
+        ready(16)
+        g = gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
+        g = ws.da[3]
+        for k in (3, 2, 1):
+            pidx, h_in, c_in, c_out, pool = _TC_BLOCKS[k - 1]
+            h_out = h_in - 2
+            self._bn_backward(k, ws, g, grads, pool, k == 3, batch * float(h_out * h_out), dbias_idx=pidx + 1)
+            ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
+            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx], accumulate=True)
+            ready(pidx)
+            g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
+        self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
+        ready(3); ready(2)
+        ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1])
+        ready(1); ready(0)
+
+    def _bn_backward(self, k: int, ws: _Workspace, g: torch.Tensor, grads, pool: bool, flatten: bool, count: float,
+                     dbias_idx: Optional[int]) -> None:
+        ext, bn = self.ext, self.bn[k]
+        gamma_idx = {0: 2, 1: 6, 2: 10, 3: 14, 4: 18}[k]
+        rows = ext.bn_bwd_reduce(ws.y[k], g, ws.coef[k], ws.part, pool, flatten)
+        ext.bn_bwd_finalize(ws.part, rows, count, bn.weight, ws.coef[k], grads[gamma_idx], grads[gamma_idx + 1],
+                            ws.bcoef[k], False)
+        dy = ws.dy[k] if k < 4 else ws.dy[4].view(ws.batch, 1, 1, 512)
+        ext.bn_bwd_apply(ws.y[k], g, ws.coef[k], ws.bcoef[k], dy, grads[dbias_idx] if dbias_idx is not None else None,
+                         pool, flatten)
+
+    # -- autograd entry ------------------------------------------------------------------------------------
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        train = self.model.training
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
+        if not needs_grad:
+            return self.forward_impl(x, train).clone()
+        return _ToyNetFunction.apply(x, self, *self.params)
+
+
+class _ToyNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fused: FusedToyNet, *params):
+        ctx.fused = fused
+        ctx.batch = x.numel() // 784
+        logits = fused.forward_impl(x, fused.model.training)
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        fused: FusedToyNet = ctx.fused
+        grads = fused.staging_grads()
+        fused._staging.zero_()
+        fused.backward_impl(ctx.batch, grads, dlogits=dlogits.contiguous().float())
+        out = []
+        for p, g in zip(fused.params, grads):
+            out.append(g.permute(0, 3, 1, 2) if p.dim() == 4 else g)
+        # fresh tensors every call so autograd may keep them (``p.grad = g`` when grad was None)
+        return (None, None, *[o.clone(memory_format=torch.preserve_format) for o in out])
+
+
+def attach(model, compute: str = "bf16") -> bool:
+    """Install the fused path on a Toy_Net living on a CUDA device."""
+    if not next(model.parameters()).is_cuda:
+        return False
+    model._fused = FusedToyNet(model, compute)
+    return True

@@ -1,0 +1,219 @@
+"""sm_100a kernel numerics vs plain PyTorch fp32 references (run on a B200: pytest -m gpu)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from ddpt_b200 import ops
+    return ops.require_native()
+
+
+def _bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _rel_err(got, want):
+    return float((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-20))
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 GEMM / conv
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k,bn", [(128, 64, 64, 64), (256, 128, 256, 128), (1024, 512, 8192, 128),
+                                      (304, 256, 512, 256), (1000, 64, 128, 64)])
+def test_linear_fwd(ext, m, n, k, bn):
+    from ddpt_b200.ops import gemm
+    x, w = _bf16(m, k, seed=1), _bf16(n, k, scale=k ** -0.5, seed=2)
+    bias = torch.randn(n, device="cuda")
+    y, _ = gemm.linear_fwd(x, w, bias, block_n=bn, out_dtype=torch.float32)
+    want = x.float() @ w.float().t() + bias
+    assert _rel_err(y, want) < 2e-3
+    yb, _ = gemm.linear_fwd(x, w, bias, relu=True, block_n=bn)
+    assert _rel_err(yb, want.relu()) < 1e-2
+
+
+def test_linear_fwd_split_k(ext):
+    from ddpt_b200.ops import gemm
+    x, w = _bf16(1024, 8192, seed=3), _bf16(512, 8192, scale=8192 ** -0.5, seed=4)
+    y, _ = gemm.linear_fwd(x, w, None, out_dtype=torch.float32, split_k=4, block_n=128)
+    assert _rel_err(y, x.float() @ w.float().t()) < 2e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 128, 128), (1024, 8192, 512), (304, 512, 64)])
+def test_linear_dgrad_mn_major_b(ext, m, n, k):
+    """dx[M,K] = dy[M,N] @ w[N,K] -- B operand consumed MN-major."""
+    from ddpt_b200.ops import gemm
+    dy, w = _bf16(m, n, seed=5), _bf16(n, k, scale=n ** -0.5, seed=6)
+    dx = gemm.linear_dgrad(dy, w)
+    assert _rel_err(dx, dy.float() @ w.float()) < 1e-2
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1024, 512, 8192), (304, 128, 256)])
+def test_linear_wgrad_mn_major_both(ext, m, n, k):
+    """dw[N,K] = dy[M,N]^T @ x[M,K] -- both operands MN-major, split-K reduction."""
+    from ddpt_b200.ops import gemm
+    dy, x = _bf16(m, n, seed=7), _bf16(m, k, seed=8)
+    want = dy.float().t() @ x.float()
+    for split in (1, None):
+        dw = gemm.linear_wgrad(dy, x, split_k=split)
+        assert _rel_err(dw, want) < 2e-3, split
+
+
+CONVS = [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512), (5, 7, 9, 64, 64)]
+
+
+def _conv_ref(x_nhwc, w_km, c_out, c_in):
+    w = w_km.float().view(c_out, 3, 3, c_in).permute(0, 3, 1, 2)
+    return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", CONVS)
+def test_conv3x3_fwd_and_stats(ext, n, h, w, ci, co):
+    from ddpt_b200.ops import gemm
+    x, wk = _bf16(n, h, w, ci, seed=9), _bf16(co, 9 * ci, scale=(9 * ci) ** -0.5, seed=10)
+    bias = torch.randn(co, device="cuda")
+    want = _conv_ref(x, wk, co, ci) + bias.view(1, -1, 1, 1)
+    y32, tiles = gemm.conv_fwd(x, wk, 3, 3, bias, out_dtype=torch.float32)
+    assert _rel_err(y32.permute(0, 3, 1, 2), want) < 2e-3
+    stats = torch.zeros(tiles * 8 * co, device="cuda")
+    y, _ = gemm.conv_fwd(x, wk, 3, 3, bias, stat_partials=stats)
+    assert _rel_err(y.permute(0, 3, 1, 2), want) < 1e-2
+    part = stats.view(tiles * 4, 2, co).sum(0)
+    flat = want.permute(0, 2, 3, 1).reshape(-1, co)
+    torch.testing.assert_close(part[0], flat.sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(flat.shape[0]))
+    torch.testing.assert_close(part[1], (flat * flat).sum(0), rtol=2e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", CONVS)
+def test_conv3x3_dgrad(ext, n, h, w, ci, co):
+    from ddpt_b200.ops import gemm
+    dy, wk = _bf16(n, h - 2, w - 2, co, seed=11), _bf16(co, 9 * ci, scale=(9 * co) ** -0.5, seed=12)
+    wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    want = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt)
+    dx = gemm.conv_dgrad(dy, wk, 3, 3)
+    assert dx.shape == (n, h, w, ci)
+    assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512)])
+def test_conv3x3_wgrad(ext, n, h, w, ci, co):
+    from ddpt_b200.ops import gemm
+    dy, x = _bf16(n, h - 2, w - 2, co, seed=13), _bf16(n, h, w, ci, seed=14)
+    xg = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wref = torch.zeros(co, ci, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(xg, wref).backward(dy.float().permute(0, 3, 1, 2))
+    want = wref.grad.permute(0, 2, 3, 1)                       # [co, kh, kw, ci]
+    for split in (1, None):
+        dw = gemm.conv_wgrad(dy, x, 3, 3, split_k=split)
+        assert _rel_err(dw, want) < 2e-3, split
+
+
+def test_toy_net_tail_batch_sizes(ext):
+    """drop_last=False tails of the reference: 304 / 332 / 608 / 664 / 784 rows."""
+    from ddpt_b200.ops import gemm
+    wk = _bf16(128, 9 * 64, scale=0.05, seed=15)
+    for b in (304, 332):
+        x = _bf16(b, 12, 12, 64, seed=b)
+        y, _ = gemm.conv_fwd(x, wk, 3, 3, out_dtype=torch.float32)
+        assert _rel_err(y.permute(0, 3, 1, 2), _conv_ref(x, wk, 128, 64)) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# amp multi-tensor kernels, fused optimizer
+# ---------------------------------------------------------------------------------------------
+def test_multi_tensor_scale_and_overflow(ext):
+    from ddpt_b200.ops import multi_tensor as mt
+    ts = [torch.randn(n, device="cuda") for n in (1, 7, 4096, 5000, 16 * 1024 * 1024 // 4 + 3)]
+    outs = [torch.empty_like(t) for t in ts]
+    flag = torch.zeros(1, device="cuda")
+    scale = torch.tensor([0.125], device="cuda")
+    mt.multi_tensor_scale(ts, outs, scale, flag)
+    for t, o in zip(ts, outs):
+        torch.testing.assert_close(o, t * 0.125, rtol=0, atol=0)
+    assert flag.item() == 0
+    ts[3][1234] = float("inf")
+    mt.multi_tensor_scale(ts, outs, scale, flag)
+    assert flag.item() == 1
+    many = [torch.randn(33, device="cuda") for _ in range(130)]     # > one launch worth of tensors
+    mo = [torch.empty_like(t) for t in many]
+    mt.multi_tensor_scale(many, mo, scale, None)
+    torch.testing.assert_close(torch.cat(mo), torch.cat(many) * 0.125, rtol=0, atol=0)
+
+
+def test_multi_tensor_axpby(ext):
+    from ddpt_b200.ops import multi_tensor as mt
+    xs = [torch.randn(n, device="cuda") for n in (5, 4100)]
+    ys = [torch.randn(n, device="cuda") for n in (5, 4100)]
+    outs = [torch.empty_like(t) for t in xs]
+    flag = torch.zeros(1, device="cuda")
+    mt.multi_tensor_axpby(xs, ys, outs, 2.0, -0.5, -1, flag)
+    for x, y, o in zip(xs, ys, outs):
+        torch.testing.assert_close(o, 2.0 * x - 0.5 * y)
+    assert flag.item() == 0
+    ys[1][7] = float("nan")
+    mt.multi_tensor_axpby(xs, ys, outs, 2.0, -0.5, 0, flag)
+    assert flag.item() == 0                                          # only x checked
+    mt.multi_tensor_axpby(xs, ys, outs, 2.0, -0.5, 1, flag)
+    assert flag.item() == 1
+
+
+def test_device_loss_scaler_protocol(ext):
+    from ddpt_b200.amp import LossScaler
+    s = LossScaler(torch.device("cuda"), dynamic=True)
+    g = torch.full((1000,), 65536.0, device="cuda")
+    s.begin_step(); s.unscale_([g]); s.update()
+    assert torch.all(g == 1.0) and s.loss_scale() == 65536.0 and not s.found_inf_host()
+    g[5] = float("inf")
+    s.begin_step(); s.unscale_([g]); s.update()
+    assert s.found_inf_host() and s.loss_scale() == 32768.0 and s.skipped_steps() == 1
+    s.load_state_dict({"scale": 4.0, "clean_steps": 1999})
+    s.begin_step(); s.unscale_([torch.ones(3, device="cuda")]); s.update()
+    assert s.loss_scale() == 8.0
+
+
+def test_fused_lookahead_sgd_matches_eager(ext):
+    """One kernel == torch-style SGD(nesterov) + reference Lookahead, incl. sync steps 1, 11, 21."""
+    import torch.nn as nn
+    from ddpt_b200 import amp
+    from ddpt_b200.ops import fused_optim
+    from ddpt_b200.optim import SGD, Lookahead
+    torch.manual_seed(0)
+    def make():
+        return nn.Sequential(nn.Conv2d(3, 8, 3), nn.Flatten(), nn.Linear(8 * 4 * 4, 5)).cuda()
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict())
+    oa = Lookahead(SGD(a.parameters(), lr=0.1, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+    ob = Lookahead(SGD(b.parameters(), lr=0.1, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+    scaler = amp.LossScaler(torch.device("cuda"))
+    assert fused_optim.attach(oa, [a], scaler)
+    fused = oa.optimizer._fused
+    for step in range(23):
+        x = torch.randn(4, 3, 6, 6, device="cuda")
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+        if step == 5:
+            oa.param_groups[0]["lr"] = ob.param_groups[0]["lr"] = 0.05     # scheduler change, no re-capture
+        if step == 7:                                                       # overflow: skip incl. counter
+            scaler.found_inf_tensor.fill_(1.0)
+            before = fused.arena.param_arena.clone()
+            oa.step()
+            assert torch.equal(before, fused.arena.param_arena)
+            scaler.found_inf_tensor.zero_()
+            continue
+        oa.step(); ob.step()
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    st = fused.state.tolist()
+    assert st[0] == 22 and st[1] == 22 % 10 and st[5] == 1
+    # bf16 shadow tracks the master weights
+    torch.testing.assert_close(fused.shadow.float(), fused.arena.param_arena, rtol=1e-2, atol=1e-3)
+    sd = oa.state_dict()
+    assert len(sd["slow_state"]) == 4 and len(sd["fast_state"]) == 4

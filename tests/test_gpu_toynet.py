@@ -1,0 +1,166 @@
+"""Fused Toy_Net (sm_100a) vs the plain PyTorch fp32 graph: forward, backward, training, engine."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+
+
+@pytest.fixture()
+def nets():
+    from ddpt_b200 import amp
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.ops import toynet_fused
+    from ddpt_b200.utils import same_seeds
+    amp.reset()
+    same_seeds(3)
+    ref = Toy_Net().cuda()
+    # non-trivial BN affine parameters so their gradients are exercised
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+    fused = copy.deepcopy(ref)
+    assert toynet_fused.attach(fused, "bf16")
+    return ref, fused
+
+
+def _batch(b, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randint(0, 256, (b, 1, 28, 28), device="cuda", generator=g, dtype=torch.uint8)
+    y = torch.randint(0, 10, (b,), device="cuda", generator=g)
+    return x, y
+
+
+@pytest.mark.parametrize("batch", [64, 304])
+def test_forward_train_and_eval_match_reference(nets, batch):
+    ref, fused = nets
+    x, _ = _batch(batch)
+    ref.train(); fused.train()
+    with torch.no_grad():
+        want = ref.forward_reference(x)
+        got = fused(x)
+    assert got.shape == (batch, 10) and _rel(got, want) < 3e-2
+    for (k, a), (_, b) in zip(fused.state_dict().items(), ref.state_dict().items()):
+        if "running" in k:
+            torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-3, msg=k)
+        if "num_batches" in k:
+            assert int(a) == int(b) == 1
+    ref.eval(); fused.eval()
+    with torch.no_grad():
+        assert _rel(fused(x), ref.forward_reference(x)) < 3e-2
+
+
+def test_backward_matches_reference(nets):
+    ref, fused = nets
+    x, y = _batch(128, seed=1)
+    ref.train(); fused.train()
+    F.cross_entropy(ref.forward_reference(x), y).backward()
+    F.cross_entropy(fused(x), y).backward()
+    names = [n for n, _ in ref.named_parameters()]
+    worst = {}
+    for n, pr, pf in zip(names, ref.parameters(), fused.parameters()):
+        assert pf.grad is not None and pf.grad.shape == pr.grad.shape, n
+        if n.endswith("bias") and (n.startswith("conv.0") or n.startswith("conv.3") or n.startswith("conv.7")
+                                    or n.startswith("conv.10") or n.startswith("dense.1")):
+            # bias followed by BatchNorm: the true gradient is 0, both sides hold rounding noise
+            assert float(pf.grad.abs().max()) < 1e-2 * float(pr.grad.abs().max() + 1e-3) + 5e-3, n
+            continue
+        worst[n] = _rel(pf.grad, pr.grad)
+    bad = {k: v for k, v in worst.items() if v > 6e-2}
+    assert not bad, bad
+
+
+def test_autograd_training_tracks_fp32_reference(nets):
+    """A few SGD steps through model(x)/loss.backward(): losses stay close to the fp32 run."""
+    ref, fused = nets
+    o_ref = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+    o_fus = torch.optim.SGD(fused.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+    ref.train(); fused.train()
+    lr_, lf_ = [], []
+    for step in range(8):
+        x, y = _batch(256, seed=100 + step % 2)
+        for net, opt, log in ((ref, o_ref, lr_), (fused, o_fus, lf_)):
+            opt.zero_grad()
+            out = net(x) if net is fused else net.forward_reference(x)
+            loss = F.cross_entropy(out, y)
+            loss.backward(); opt.step(); log.append(float(loss))
+    assert lf_[-1] < lf_[0] * 0.8
+    for a, b in zip(lr_, lf_):
+        assert abs(a - b) < 0.08 * max(abs(a), 0.1)
+
+
+def test_step_engine_graph_matches_eager_engine_and_trains():
+    """iterate_loader through the CUDA-graph engine: loss falls, Q1 scaling holds, graph == eager."""
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.data import BatchLoader, synthetic_mnist
+    from ddpt_b200.engine import iterate_loader
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.utils import same_seeds
+    results = {}
+    for use_graph in (False, True):
+        amp.reset()
+        same_seeds(5)
+        model = Toy_Net().cuda()
+        opt = Lookahead(SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+        loss_fn = nn.CrossEntropyLoss()
+        assert ops.attach_step_engine(model, loss_fn, opt, use_graph=use_graph)
+        data = synthetic_mnist(2048 + 304, seed=1)
+        loader = BatchLoader(data, 256, None, torch.device("cuda"), mode="device")
+        loader.quiet = True
+        hist = []
+        for epoch in range(3):
+            model.train()
+            hist.append(iterate_loader(loader, model, loss_fn, 0, opt, training=True))
+        model.eval()
+        with torch.no_grad():
+            v = iterate_loader(loader, model, loss_fn, 0, None, training=False)
+        eng = model._ddpt_step_engine
+        results[use_graph] = (hist, v, eng.graph_replays)
+        assert hist[-1][0] < hist[0][0] * 0.7, hist                  # learns
+        assert 0.5 < hist[0][0] * 256 < 3.0                          # Q1: logged loss is CE / B
+        assert hist[0][2] == 0.1 and 0 <= v[1] <= 1
+        st = amp.current_state().scaler.state_dict()
+        assert st["scale"] == 65536.0 and st["skipped"] == 0
+    assert results[True][2] > 0 and results[False][2] == 0
+    for (a, b) in zip(results[True][0], results[False][0]):
+        assert abs(a[0] - b[0]) < 0.05 * abs(b[0]) and abs(a[1] - b[1]) < 0.05
+    amp.reset()
+
+
+def test_engine_overflow_skips_step_and_halves_scale():
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    amp.reset()
+    model = Toy_Net().cuda()
+    opt = Lookahead(SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+    model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+    loss_fn = nn.CrossEntropyLoss()
+    assert ops.attach_step_engine(model, loss_fn, opt)
+    eng = model._ddpt_step_engine
+    x, y = _batch(64)
+    model.train()
+    eng.begin_pass()
+    for _ in range(3):
+        eng.run(x, y, True)                                          # eager, capture, replay
+    fo = opt.optimizer._fused
+    before = fo.arena.param_arena.clone()
+    with torch.no_grad():
+        model.dense[4].bias.fill_(float("nan"))                      # poisons logits -> inf/nan gradients
+    poisoned = fo.arena.param_arena.clone()
+    eng.run(x, y, True)
+    assert torch.equal(torch.nan_to_num(fo.arena.param_arena), torch.nan_to_num(poisoned))   # step skipped
+    sd = amp.current_state().scaler.state_dict()
+    assert sd["scale"] == 32768.0 and sd["skipped"] == 1
+    assert fo.state.tolist()[5] == 1 and fo.state.tolist()[0] == 3
+    amp.reset()
