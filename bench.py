@@ -317,10 +317,13 @@ def run_reference(args):
         lookahead = ref_utils.Lookahead(optimizer=optimizer, k=10, alpha=0.5)
         # torch>=2 compat for the vendored Lookahead (never calls Optimizer.__init__): give it the
         # attributes Optimizer.zero_grad needs -- done from outside, the source file is untouched.
-        torch.optim.Optimizer.__init__(lookahead, optimizer.param_groups, {})
-        lookahead.param_groups = optimizer.param_groups
-        for gdict in lookahead.param_groups:
-            gdict.setdefault("counter", 0)
+        from collections import OrderedDict
+        lookahead.defaults = {}
+        lookahead._zero_grad_profile_name = "Optimizer.zero_grad#Lookahead.zero_grad"
+        for hook_attr in ("_optimizer_step_pre_hooks", "_optimizer_step_post_hooks",
+                          "_optimizer_state_dict_pre_hooks", "_optimizer_state_dict_post_hooks",
+                          "_optimizer_load_state_dict_pre_hooks", "_optimizer_load_state_dict_post_hooks"):
+            setattr(lookahead, hook_attr, OrderedDict())
         loss_function = nn.CrossEntropyLoss()
         model, apex_optimizer = ref_amp.initialize(model, optimizers=lookahead, opt_level="O1")
         parallel_model = DDP(model, device_ids=[local], output_device=local)

@@ -5,6 +5,7 @@
 void ddpt_bind_nn(pybind11::module_& m);
 void ddpt_bind_comm(pybind11::module_& m);
 void ddpt_bind_loader(pybind11::module_& m);
+void ddpt_bind_reducer(pybind11::module_& m);
 
 void ddpt_bind_extra(pybind11::module_& m) {
 #ifdef DDPT_HAVE_NN
@@ -15,5 +16,8 @@ void ddpt_bind_extra(pybind11::module_& m) {
 #endif
 #ifdef DDPT_HAVE_LOADER
   ddpt_bind_loader(m);
+#endif
+#ifdef DDPT_HAVE_REDUCER
+  ddpt_bind_reducer(m);
 #endif
 }

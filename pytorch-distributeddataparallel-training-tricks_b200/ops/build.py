@@ -81,6 +81,8 @@ def feature_defines(cu: List[str], cpp: List[str]) -> List[str]:
         defs.append("-DDDPT_HAVE_COMM")
     if "bindings_loader.cpp" in names:
         defs.append("-DDDPT_HAVE_LOADER")
+    if "reducer.cpp" in names:
+        defs.append("-DDDPT_HAVE_REDUCER")
     return defs
 
 

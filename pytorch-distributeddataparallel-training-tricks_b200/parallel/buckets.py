@@ -68,7 +68,7 @@ def plan_buckets(params: Sequence[torch.Tensor], bucket_cap_mb: float = 25.0,
         inner = 0
         for n in b.numels:
             b.offsets.append(cursor + inner)
-            inner += _round_up(n, 4)  # keep every tensor 16-byte aligned
+            inner += _round_up(n, 32)  # 128 B (fp32) / 64 B (bf16 shadow) alignment: TMA needs >= 16 B bases
         b.numel = _round_up(inner, ALIGN_ELEMS)
         cursor += b.numel
     return buckets

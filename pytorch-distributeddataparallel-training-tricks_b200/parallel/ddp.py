@@ -30,7 +30,7 @@ import torch.nn as nn
 
 from .arena import FlatArena
 from .buckets import plan_buckets
-from .reducer import ProcessGroupBackend, Reducer
+from .reducer import ProcessGroupBackend, make_reducer
 
 
 def _flat_broadcast(tensors: List[torch.Tensor], src: int, group) -> None:
@@ -96,7 +96,7 @@ class DistributedDataParallel(nn.Module):
         if hasattr(backend, "bind"):
             backend.bind(self.arena)
         self._sync_module_states()
-        self.reducer = Reducer(self.arena, backend)
+        self.reducer = make_reducer(self.arena, backend, process_group)
         self._buffers_dirty = True  # mirrors torch's require_forward_param_sync
         from ..amp import current_state
         current_state().reducers.append(self.reducer)

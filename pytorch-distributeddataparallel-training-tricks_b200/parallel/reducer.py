@@ -135,3 +135,59 @@ class Reducer:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+
+
+class NativeReducerAdapter:
+    """The C++ reducer (csrc/reducer/reducer.cpp) behind the same interface as :class:`Reducer`."""
+
+    def __init__(self, ext, arena: FlatArena, backend, process_group=None):
+        self.arena = arena
+        self.backend = backend
+        self.buckets = arena.buckets
+        self._native = ext.NativeReducer(list(arena.params), list(arena.grad_views), arena.grad_arena,
+                                         [list(b.param_indices) for b in self.buckets],
+                                         [b.start for b in self.buckets], [b.numel for b in self.buckets])
+        if getattr(backend, "fuses_unscale", False):
+            r = backend.region
+            self._native.use_fused(r.peer_ptrs, r.signal_ptrs, r.mc_ptr, r.rank, backend.algo, backend._unit)
+        else:
+            pg = process_group if process_group is not None else dist.distributed_c10d._get_default_group()
+            self._native.use_process_group(pg)
+        self.native = True
+
+    def expect_scaled_grads(self, scaler) -> None:
+        fuse = getattr(self.backend, "fuses_unscale", False) and scaler is not None and scaler.on_device
+        self._native.expect_scaled_grads(scaler.state if fuse else None)
+
+    def consumed_scaler(self) -> bool:
+        return self._native.consumed_scaler()
+
+    def prepare_for_backward(self) -> None:
+        self._native.prepare_for_backward()
+
+    @property
+    def require_sync(self) -> bool:
+        return self._native.require_sync
+
+    @require_sync.setter
+    def require_sync(self, value: bool) -> None:
+        self._native.require_sync = bool(value)
+
+    @property
+    def stats(self) -> dict:
+        return {"launches": self._native.launches, "steps": self._native.steps,
+                "folded_copies": self._native.folded_copies}
+
+    def remove_hooks(self) -> None:
+        self._native.require_sync = False
+
+
+def make_reducer(arena: FlatArena, backend, process_group=None, prefer_native: bool = True):
+    """Native C++ reducer when the extension is importable (CPU or CUDA), else the Python one."""
+    import os
+    if prefer_native and os.environ.get("DDPT_PY_REDUCER") != "1":
+        from ..ops import load_ext
+        ext = load_ext()
+        if ext is not None and hasattr(ext, "NativeReducer"):
+            return NativeReducerAdapter(ext, arena, backend, process_group)
+    return Reducer(arena, backend)

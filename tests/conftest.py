@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# single-GPU multi-"rank" simulations launch co-operating kernels on many streams: give every stream its own
+# hardware queue so that one spinning kernel cannot be queued in front of the kernel it waits for.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REFERENCE = "/root/reference"
 
 

@@ -37,6 +37,9 @@ def _grads_equal_average(rank, world):
     for w, p in zip(want, model.parameters()):
         torch.testing.assert_close(p.grad, w, rtol=1e-5, atol=1e-6)
     assert ddp.reducer.stats["launches"] == len(ddp.buckets)
+    import os
+    if os.environ.get("DDPT_PY_REDUCER") != "1":
+        assert getattr(ddp.reducer, "native", False), "the C++ reducer should be active when the extension is built"
 
     # no_sync: local gradient only, next synced backward folds it in
     ddp.zero_grad()
