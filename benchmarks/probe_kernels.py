@@ -49,12 +49,15 @@ def main():
             dy = torch.randn(B, h - 2, w - 2, co, device="cuda").bfloat16()
             flops = 2.0 * B * (h - 2) * (w - 2) * co * ci * 9
             for bn in (64, 128, 256):
-                if co % bn == 0:
-                    t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn), flush=flush)
-                    rows.append(dict(op=f"{name}.fwd", block_n=bn, ms=t, tflops=flops / t / 1e9))
+                for pers in (False, True):
+                    tag = ".persist" if pers else ""
+                    if co % bn == 0:
+                        t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn, persistent=pers), flush=flush)
+                        rows.append(dict(op=f"{name}.fwd{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
+                    if ci % bn == 0:
+                        t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn, persistent=pers), flush=flush)
+                        rows.append(dict(op=f"{name}.dgrad{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                 if ci % bn == 0:
-                    t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn), flush=flush)
-                    rows.append(dict(op=f"{name}.dgrad", block_n=bn, ms=t, tflops=flops / t / 1e9))
                     dw = torch.zeros(co, 3, 3, ci, device="cuda")
                     t = timeit(lambda: gemm.conv_wgrad(dy, x, 3, 3, out=dw, block_n=bn), flush=flush)
                     rows.append(dict(op=f"{name}.wgrad", block_n=bn, ms=t, tflops=flops / t / 1e9))

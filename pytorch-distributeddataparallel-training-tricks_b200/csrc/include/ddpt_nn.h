@@ -42,6 +42,8 @@ struct ConvGemmProblem {
 
 // block_n in {64, 128, 256}; returns the number of M tiles launched.
 int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
+// Persistent variant (one CTA per SM, double-buffered TMEM accumulator); no split-K.
+int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
 
 // Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,
 // reduction over the pixel bricks; fp32 accumulate into a zero-initialised or beta=1 output).

@@ -1,0 +1,332 @@
+// Persistent implicit-GEMM convolution / linear forward and data-gradient for sm_100a.
+//
+// Replaces cuDNN convolution fwd/dgrad and cuBLAS linear fwd/dgrad of the reference stack
+// (Toy_Net layers K3/K6/K8/K11/K13).  One CTA per SM walks a static list of
+// 128 x BLOCK_N output tiles; the accumulator is double-buffered in TMEM so the epilogue of tile i
+// overlaps the TMA/MMA main loop of tile i+1 and the one-time setup (barriers, TMEM allocation,
+// descriptor prefetch) is paid once per SM instead of once per tile:
+//
+//   warp 0      TMA producer: per K block (one filter tap x 64 input channels) one 4-D box load of
+//               the activation brick shifted by the tap, plus the matching weight tile
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per K block),
+//               tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, each owning half of the columns): tcgen05.ld 32 columns at a time, + bias, ReLU, BatchNorm partial
+//               statistics (column sum / sum of squares per tile), bf16 or fp32 store
+//
+// Operands are staged in 128-byte-swizzled shared memory exactly as TMA writes them; the matrix
+// descriptors describe that layout (K-major for activations, K- or MN-major for weights).
+#include <cuda.h>
+#include "../include/ddpt_nn.h"
+#include "../include/ddpt_common.cuh"
+#include "../include/umma.cuh"
+#include "tensor_map.h"
+#include <stdexcept>
+
+namespace ddpt {
+namespace {
+
+using namespace umma;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 320;               // producer, mma, 8 epilogue warps
+constexpr int kEpilogueWarps = 8;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
+
+template <int BN> __host__ __device__ constexpr int stages_for() { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+
+struct KernelArgs {
+  int tiles_w, tiles_h;
+  int box_w, box_h, box_n;
+  int out_w, out_h, out_n;
+  int taps_w, num_taps, tap_sign, a_h_off, a_w_off;
+  int k_chunks;                 // reduction channels / 64
+  int n_total;
+  long long ld_out;
+  void* out;
+  const float* bias;
+  float* stat_partials;
+  int relu, out_fp32, a_rows_bytes;
+};
+
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                            const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
+  constexpr int kStages = stages_for<BN>();
+  constexpr int kBStageBytes = BN * kBlockK * 2;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+  constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kAStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * kBStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;               // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int total_kb = args.num_taps * args.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx_bytes = args.a_rows_bytes + kBStageBytes;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+        const int tw = tile_m % args.tiles_w;
+        const int th = (tile_m / args.tiles_w) % args.tiles_h;
+        const int tn = tile_m / (args.tiles_w * args.tiles_h);
+        const int w0 = tw * args.box_w, h0 = th * args.box_h, n0 = tn * args.box_n;
+        const int col0 = tile_n * BN;
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t phase = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1, 1);
+          const int tap = kb / args.k_chunks;
+          const int chunk = kb - tap * args.k_chunks;
+          const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_4d(smem_a + s * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
+                      w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
+          if (!B_MN) {
+            tma_load_2d(smem_b + s * kBStageBytes, &tmap_b, &full_bar[s], kb * kBlockK, col0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(smem_b + s * kBStageBytes + j * (kBlockK * 128), &tmap_b, &full_bar[s],
+                          tap * args.n_total + col0 + j * 64, chunk * kBlockK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t phase = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], phase, 2);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * kAStageBytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * kBStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
+                                        : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
+            mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit(&empty_bar[s]);
+        }
+        mma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..9; quadrant = warp & 3, column half = (warp - 2) >> 2 =====
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int box_hw = args.box_h * args.box_w;
+    const int dn = row / box_hw, rem = row - dn * box_hw;
+    const int dh = rem / args.box_w, dw = rem - dh * args.box_w;
+    constexpr int kChunksPerWarp = (BN / 32) / 2;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+      const int tw = tile_m % args.tiles_w;
+      const int th = (tile_m / args.tiles_w) % args.tiles_h;
+      const int tn = tile_m / (args.tiles_w * args.tiles_h);
+      const int n = tn * args.box_n + dn, h = th * args.box_h + dh, w = tw * args.box_w + dw;
+      const bool valid = dn < args.box_n && n < args.out_n && h < args.out_h && w < args.out_w;
+      const long long out_row = (static_cast<long long>(n) * args.out_h + h) * args.out_w + w;
+      const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase, 3);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int c = half * kChunksPerWarp + cc;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const int col = tile_n * BN + c * 32;
+        if (args.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
+        }
+        if (args.stat_partials != nullptr) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s1[j] = valid ? f[j] : 0.f;
+            s2[j] = s1[j] * s1[j];
+          }
+#pragma unroll
+          for (int width = 16; width >= 1; width >>= 1) {
+            const bool upper = (lane & width) != 0;
+#pragma unroll
+            for (int j = 0; j < width; ++j) {
+              float keep1 = upper ? s1[j + width] : s1[j];
+              float give1 = upper ? s1[j] : s1[j + width];
+              float keep2 = upper ? s2[j + width] : s2[j];
+              float give2 = upper ? s2[j] : s2[j + width];
+              s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, give1, width);
+              s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, width);
+            }
+          }
+          float* dst = args.stat_partials + (static_cast<long long>(tile_m) * 4 + quad) * 2 * args.n_total;
+          dst[col + lane] = s1[0];
+          dst[args.n_total + col + lane] = s2[0];
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (args.out_fp32) {
+            float* o = static_cast<float*>(args.out) + out_row * args.ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(args.out) + out_row * args.ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(f[j], f[j + 1]);
+              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool B_MN>
+int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
+  constexpr int kStages = stages_for<BN>();
+  constexpr int kBStageBytes = BN * kBlockK * 2;
+  const size_t smem_bytes = 1024 + kStages * (kAStageBytes + kBStageBytes) + (2 * kStages + 4) * 8 + 16;
+
+  KernelArgs a{};
+  a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
+  a.out_w = p.out_w; a.out_h = p.out_h; a.out_n = p.out_n;
+  a.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;
+  a.tiles_h = (p.out_h + p.box_h - 1) / p.box_h;
+  const int tiles_n = (p.out_n + p.box_n - 1) / p.box_n;
+  a.taps_w = p.taps_w; a.num_taps = p.taps_h * p.taps_w; a.tap_sign = p.tap_sign;
+  a.a_h_off = p.a_h_off; a.a_w_off = p.a_w_off;
+  a.k_chunks = p.a_c / kBlockK;
+  a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
+  a.stat_partials = p.stat_partials; a.relu = p.relu; a.out_fp32 = p.out_fp32;
+  a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
+
+  if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)
+    throw std::runtime_error("conv_gemm: unsupported shape (C % 64, N % BLOCK_N, brick <= 128 rows)");
+  if (p.split_k > 1) throw std::runtime_error("conv_gemm (persistent): split_k is handled by the non-persistent kernel");
+
+  // A: (C, W, H, N) bf16, box (64, box_w, box_h, box_n), 128B swizzle, OOB -> 0
+  const uint64_t a_dims[4] = {(uint64_t)p.a_c, (uint64_t)p.a_w, (uint64_t)p.a_h, (uint64_t)p.a_n};
+  const uint64_t a_strides[3] = {(uint64_t)p.a_c * 2, (uint64_t)p.a_c * p.a_w * 2,
+                                 (uint64_t)p.a_c * p.a_w * p.a_h * 2};
+  const uint32_t a_box[4] = {(uint32_t)kBlockK, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
+  CUtensorMap tmap_a = make_tensor_map_bf16(p.a, 4, a_dims, a_strides, a_box);
+
+  CUtensorMap tmap_b;
+  if (!B_MN) {
+    const uint64_t b_dims[2] = {(uint64_t)a.num_taps * p.a_c, (uint64_t)p.n_total};
+    const uint64_t b_strides[1] = {(uint64_t)p.b_ld * 2};
+    const uint32_t b_box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
+  } else {
+    const uint64_t b_dims[2] = {(uint64_t)a.num_taps * p.n_total, (uint64_t)p.a_c};
+    const uint64_t b_strides[1] = {(uint64_t)p.b_ld * 2};
+    const uint32_t b_box[2] = {64u, (uint32_t)kBlockK};
+    tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
+  }
+
+  auto kernel = conv_gemm_persistent_kernel<BN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    configured = true;
+  }
+  const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
+  const int tiles_n_cols = p.n_total / BN;
+  const int total_tiles = tiles_m * tiles_n_cols;
+  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+  return tiles_m;
+}
+
+}  // namespace
+
+int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream) {
+  if (p.b_mn_major) {
+    switch (block_n) {
+      case 64: return launch_persistent_impl<64, true>(p, stream);
+      case 128: return launch_persistent_impl<128, true>(p, stream);
+      case 256: return launch_persistent_impl<256, true>(p, stream);
+    }
+  } else {
+    switch (block_n) {
+      case 64: return launch_persistent_impl<64, false>(p, stream);
+      case 128: return launch_persistent_impl<128, false>(p, stream);
+      case 256: return launch_persistent_impl<256, false>(p, stream);
+    }
+  }
+  throw std::runtime_error("conv_gemm: block_n must be 64, 128 or 256");
+}
+
+}  // namespace ddpt

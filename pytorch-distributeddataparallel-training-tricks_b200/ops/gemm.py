@@ -12,6 +12,7 @@ conventions used throughout the fused Toy_Net path:
 from __future__ import annotations
 
 import functools
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -42,6 +43,13 @@ def pick_box(out_n: int, out_h: int, out_w: int, multiple_of: int = 1, max_rows:
     return best
 
 
+def use_persistent(flag: Optional[bool] = None) -> bool:
+    """Persistent (one CTA per SM, double-buffered TMEM) GEMM kernels; DDPT_GEMM_PERSISTENT=0 disables."""
+    if flag is not None:
+        return flag
+    return os.environ.get("DDPT_GEMM_PERSISTENT", "1") != "0"
+
+
 def _block_n(n_total: int, prefer: Optional[int]) -> int:
     if prefer is not None:
         return prefer
@@ -53,7 +61,8 @@ def _block_n(n_total: int, prefer: Optional[int]) -> int:
 
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-             block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1):
+             block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,
+             persistent: Optional[bool] = None):
     """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
     ext = require_native()
     n, h, w, c = x.shape
@@ -63,12 +72,12 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
         out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
     box = pick_box(n, ho, wo)
     tiles = ext.conv_gemm(x, w_km, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], 1, [0, 0], False,
-                          bias, relu, stat_partials, split_k, _block_n(c_out, block_n))
+                          bias, relu, stat_partials, split_k, _block_n(c_out, block_n), use_persistent(persistent))
     return out, tiles
 
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
-               block_n: Optional[int] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None):
     """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
@@ -78,7 +87,7 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
     box = pick_box(n, h, w)
     ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
-                  None, False, None, 1, _block_n(c_in, block_n))
+                  None, False, None, 1, _block_n(c_in, block_n), use_persistent(persistent))
     return out
 
 
@@ -105,17 +114,19 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
                stat_partials: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-               block_n: Optional[int] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None):
     """y [M, N] = x [M, K] @ w [N, K]^T (+ bias)."""
     m, k = x.shape
-    y, tiles = conv_fwd(x.view(1, 1, m, k), w, 1, 1, bias, relu, stat_partials, None, block_n, out_dtype, split_k)
+    y, tiles = conv_fwd(x.view(1, 1, m, k), w, 1, 1, bias, relu, stat_partials, None, block_n, out_dtype, split_k,
+                        persistent)
     return y.view(m, w.shape[0]), tiles
 
 
-def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None):
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None,
+                 persistent: Optional[bool] = None):
     """dx [M, K] = dy [M, N] @ w [N, K]."""
     m, n = dy.shape
-    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n).view(m, w.shape[1])
+    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n, persistent).view(m, w.shape[1])
 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,

@@ -58,9 +58,10 @@ def test_simulated_ranks_reduce_in_place(ext, world, algo, numel):
 
 
 def test_all_ranks_bit_identical_and_scaled(ext):
-    bufs, states = _simulate(ext, 4, 8192 * 8, 2, scale_state=True, offset=128)
+    numel, offset = 8192 * 8, 128
+    bufs, states = _simulate(ext, 4, numel, 2, scale_state=True, offset=offset)
     for b in bufs[1:]:
-        assert torch.equal(bufs[0], b)
+        assert torch.equal(bufs[0][offset:offset + numel], b[offset:offset + numel])
     assert all(float(s[2]) == 0.0 for s in states)
 
 

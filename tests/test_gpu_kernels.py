@@ -14,6 +14,13 @@ def ext():
     return ops.require_native()
 
 
+@pytest.fixture(params=["persistent", "per_tile"], autouse=True)
+def gemm_flavour(request, monkeypatch):
+    """Every GEMM/conv test runs against both forward/dgrad kernels (persistent and one-CTA-per-tile)."""
+    monkeypatch.setenv("DDPT_GEMM_PERSISTENT", "1" if request.param == "persistent" else "0")
+    return request.param
+
+
 def _bf16(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)

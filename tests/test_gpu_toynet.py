@@ -59,22 +59,29 @@ def test_forward_train_and_eval_match_reference(nets, batch):
 
 
 def test_backward_matches_reference(nets):
+    """Gradients vs the fp32 graph, judged against what bf16 itself costs: a torch bf16-autocast run of the
+    same network is the yardstick (bf16 activations + BatchNorm backward cancellations put both ~10-20 %
+    from fp32 at this batch size; see profiles/toynet_grad_error_vs_fp32.txt)."""
     ref, fused = nets
+    auto = copy.deepcopy(ref)
     x, y = _batch(128, seed=1)
-    ref.train(); fused.train()
+    ref.train(); fused.train(); auto.train()
     F.cross_entropy(ref.forward_reference(x), y).backward()
     F.cross_entropy(fused(x), y).backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = auto.forward_reference(x)
+    F.cross_entropy(out.float(), y).backward()
     names = [n for n, _ in ref.named_parameters()]
-    worst = {}
-    for n, pr, pf in zip(names, ref.parameters(), fused.parameters()):
+    bad = {}
+    for n, pr, pf, pa in zip(names, ref.parameters(), fused.parameters(), auto.parameters()):
         assert pf.grad is not None and pf.grad.shape == pr.grad.shape, n
-        if n.endswith("bias") and (n.startswith("conv.0") or n.startswith("conv.3") or n.startswith("conv.7")
-                                    or n.startswith("conv.10") or n.startswith("dense.1")):
-            # bias followed by BatchNorm: the true gradient is 0, both sides hold rounding noise
-            assert float(pf.grad.abs().max()) < 1e-2 * float(pr.grad.abs().max() + 1e-3) + 5e-3, n
+        if n.endswith("bias") and n.split(".")[0] + "." + n.split(".")[1] in ("conv.0", "conv.3", "conv.7", "conv.10", "dense.1"):
+            # bias followed by BatchNorm: the true gradient is exactly 0, every implementation holds rounding noise
+            assert float(pf.grad.abs().max()) < 1e-2, n
             continue
-        worst[n] = _rel(pf.grad, pr.grad)
-    bad = {k: v for k, v in worst.items() if v > 6e-2}
+        e_fused, e_auto = _rel(pf.grad, pr.grad), _rel(pa.grad, pr.grad)
+        if e_fused > 1.35 * e_auto + 0.01:
+            bad[n] = (e_fused, e_auto)
     assert not bad, bad
 
 
