@@ -1,0 +1,79 @@
+"""Gradient all-reduce bandwidth sweep (BASELINE.json config 5): fused NVLink kernel vs NCCL.
+
+    torchrun --nproc-per-node N benchmarks/allreduce_sweep.py [--out gpurun_out/allreduce_sweep_nN.json]
+
+Buckets 64 KB - 256 MB fp32.  Device-timed (CUDA events), max over ranks, L2 flushed between iterations.
+bus GB/s = 2 (n-1)/n * bytes / time (the NCCL convention); the roofline is the measured 770 GB/s per
+direction per GPU (900 nominal)."""
+import argparse, json, os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from ddpt_b200.ops import require_native
+    from ddpt_b200.parallel.symm import SymmetricRegion
+    ext = require_native()
+    max_elems = 256 * 1024 * 1024 // 4
+    region = SymmetricRegion(max_elems, dev)
+    state = torch.tensor([1.0, 1.0, 0.0, 0.0, 0.0], device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    nccl_buf = torch.randn(max_elems, device=dev)
+    region.tensor.copy_(nccl_buf)
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            torch.cuda.synchronize(); dist.barrier()
+            s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rows = []
+    size = 64 * 1024
+    while size <= 256 * 1024 * 1024:
+        n = size // 4
+        row = {"bytes": size}
+        algos = {"auto": 0, "twoshot": 2}
+        if n <= 64 * 1024:
+            algos["oneshot"] = 1
+        if region.mc_ptr:
+            algos["multimem"] = 3
+        for name, algo in algos.items():
+            ms = timed(lambda: ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, rank, 0, n,
+                                                   state, state[2:3], 0, algo, 0, 20000), a.iters)
+            row[f"fused_{name}_us"] = ms * 1e3
+            row[f"fused_{name}_busGBs"] = 2 * (world - 1) / world * size / (ms * 1e-3) / 1e9
+        view = nccl_buf[:n]
+        ms = timed(lambda: dist.all_reduce(view), a.iters)
+        row["nccl_us"] = ms * 1e3
+        row["nccl_busGBs"] = 2 * (world - 1) / world * size / (ms * 1e-3) / 1e9
+        rows.append(row)
+        size *= 4
+    if rank == 0:
+        out = {"world": world, "provider": region.provider, "multicast": bool(region.mc_ptr), "rows": rows,
+               "link_GBs_measured_per_direction": 770, "link_GBs_nominal": 900}
+        print(json.dumps(out, indent=1))
+        if a.out:
+            os.makedirs(os.path.dirname(a.out), exist_ok=True)
+            json.dump(out, open(a.out, "w"), indent=1)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,7 +42,8 @@ struct ConvGemmProblem {
 
 // block_n in {64, 128, 256}; returns the number of M tiles launched.
 int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
-// Persistent variant (one CTA per SM, double-buffered TMEM accumulator); no split-K.
+// Persistent variant (one CTA per SM, double-buffered TMEM accumulator); no split-K.  With stat_partials the
+// statistics are accumulated per CTA and the return value is the number of row groups written (= grid size).
 int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
 
 // Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,

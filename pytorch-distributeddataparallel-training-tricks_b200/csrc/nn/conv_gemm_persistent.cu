@@ -164,6 +164,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int dn = row / box_hw, rem = row - dn * box_hw;
     const int dh = rem / args.box_w, dw = rem - dh * args.box_w;
     constexpr int kChunksPerWarp = (BN / 32) / 2;
+    // BatchNorm statistics: lane L accumulates column (chunk*32 + L) over every tile of this CTA.  The launcher
+    // sizes the grid as a multiple of num_n_tiles, so a CTA always works on the same column block.
+    float acc_s1[kChunksPerWarp], acc_s2[kChunksPerWarp];
+#pragma unroll
+    for (int cc = 0; cc < kChunksPerWarp; ++cc) acc_s1[cc] = acc_s2[cc] = 0.f;
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
@@ -210,9 +215,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
               s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, width);
             }
           }
-          float* dst = args.stat_partials + (static_cast<long long>(tile_m) * 4 + quad) * 2 * args.n_total;
-          dst[col + lane] = s1[0];
-          dst[args.n_total + col + lane] = s2[0];
+          acc_s1[cc] += s1[0];
+          acc_s2[cc] += s2[0];
         }
         if (args.relu) {
 #pragma unroll
@@ -242,6 +246,19 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (args.stat_partials != nullptr) {
+      // one row group per CTA: [blockIdx.x][quad][2][n_total]; columns of other column blocks are written as 0
+      const int my_tile_n = blockIdx.x % num_n_tiles;
+      float* dst = args.stat_partials + (static_cast<long long>(blockIdx.x) * 4 + quad) * 2 * args.n_total;
+      for (int tn2 = 0; tn2 < num_n_tiles; ++tn2) {
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+          const int col = tn2 * BN + (half * kChunksPerWarp + cc) * 32 + lane;
+          dst[col] = tn2 == my_tile_n ? acc_s1[cc] : 0.f;
+          dst[args.n_total + col] = tn2 == my_tile_n ? acc_s2[cc] : 0.f;
+        }
+      }
     }
   }
 
@@ -304,10 +321,12 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
   const int tiles_n_cols = p.n_total / BN;
   const int total_tiles = tiles_m * tiles_n_cols;
-  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  grid -= grid % tiles_n_cols;                 // a CTA keeps one column block (statistics accumulate in registers)
+  if (grid < tiles_n_cols) grid = tiles_n_cols;
   kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
   DDPT_CUDA_CHECK(cudaGetLastError());
-  return tiles_m;
+  return p.stat_partials != nullptr ? grid : tiles_m;   // statistic row groups (x4 rows) written
 }
 
 }  // namespace

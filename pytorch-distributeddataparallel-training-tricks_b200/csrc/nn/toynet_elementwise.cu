@@ -333,8 +333,36 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
   load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_dz[j] = s_dzx[j] = 0.f;
-  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix;
-       pix += (long long)gridDim.x * rows_per_blk) {
+  const long long stride = (long long)gridDim.x * rows_per_blk;
+  if (!POOL && !k.flatten) {
+    constexpr int U = 4;                                  // independent 16-byte loads in flight per thread: 2*U
+    for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
+      uint4 yv[U], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * stride;
+        if (pix < total_pix) {
+          yv[u] = ldg16(k.y + pix * k.c + v * 8);
+          gv[u] = ldg16(k.g + pix * k.c + v * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix0 + u * stride >= total_pix) continue;
+        float f[8], g[8];
+        unpack8(yv[u], f);
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float dz = z > 0.f ? g[j] : 0.f;
+          s_dz[j] += dz;
+          s_dzx[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s_dzx[j]);
+        }
+      }
+    }
+  } else
+  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
     const int pw = (int)(pix % ow);
     const int ph = (int)((pix / ow) % oh);
     const long long img = pix / ((long long)ow * oh);
@@ -355,10 +383,13 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
       float best[8], besty[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }     // z <= 0 everywhere -> no gradient
+      uint4 yq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yq[q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float f[8];
-        unpack8(ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c), f);
+        unpack8(yq[q], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[j], sc[j], sh[j]);
@@ -427,8 +458,38 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
   load8f(coef + v * 8, c1); load8f(coef + k.c + v * 8, c2); load8f(coef + 2 * k.c + v * 8, c3);
 #pragma unroll
   for (int j = 0; j < 8; ++j) db[j] = 0.f;
-  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix;
-       pix += (long long)gridDim.x * rows_per_blk) {
+  const long long stride = (long long)gridDim.x * rows_per_blk;
+  if (!POOL && !k.flatten) {
+    constexpr int U = 4;
+    for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
+      uint4 yv[U], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * stride;
+        if (pix < total_pix) {
+          yv[u] = ldg16(k.y + pix * k.c + v * 8);
+          gv[u] = ldg16(k.g + pix * k.c + v * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * stride;
+        if (pix >= total_pix) continue;
+        float f[8], g[8], o[8];
+        unpack8(yv[u], f);
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float dz = z > 0.f ? g[j] : 0.f;
+          o[j] = c1[j] * (dz - c2[j] - (f[j] - mu[j]) * is[j] * c3[j]);
+          db[j] += o[j];
+        }
+        *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
+      }
+    }
+  } else
+  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
     const int pw = (int)(pix % ow);
     const int ph = (int)((pix / ow) % oh);
     const long long img = pix / ((long long)ow * oh);
@@ -447,6 +508,9 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
     } else {
       const long long base_off = ((img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
+      uint4 yq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yq[q] = ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c);
       float f[4][8];
       float best[8];
       int arg[8];
@@ -454,7 +518,7 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        unpack8(ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c), f[q]);
+        unpack8(yq[q], f[q]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[q][j], sc[j], sh[j]);
