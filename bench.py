@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line contract)
+
 METRIC = "MNIST Toy_Net training images/sec (whole job, device-timed, max over ranks)"
 BATCH = 1024
 
@@ -220,7 +223,7 @@ def run_ours(args):
     ms_dev = max_over_ranks(start.elapsed_time(stop), world)
     clocks = sampler.stop() if rank == 0 else {}
     replays = engine.graph_replays - replays0
-    launches_per_step = engine.fused_model.count_launches(B) if hasattr(engine.fused_model, "count_launches") else 0
+    launches_per_step = engine.fused_model.count_launches(B) + (len(model.buckets) if world > 1 else 0)
 
     # ---- (2) end to end through the public API: pinned host batches in, metrics out every step ---------
     engine.host_metrics_every_step = True

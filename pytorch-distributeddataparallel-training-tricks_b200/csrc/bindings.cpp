@@ -160,7 +160,10 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
   if (p.stat_partials != nullptr) {
     const int64_t tiles = (int64_t)((p.out_w + p.box_w - 1) / p.box_w) * ((p.out_h + p.box_h - 1) / p.box_h) *
                           ((p.out_n + p.box_n - 1) / p.box_n);
-    TORCH_CHECK(stat_partials->numel() >= tiles * 8 * p.n_total, "stat_partials too small");
+    // persistent kernel: one row group per CTA (grid <= #SMs, may exceed the M-tile count when N is split)
+    const int64_t n_tiles = p.n_total / block_n;
+    const int64_t groups = std::max<int64_t>(tiles, std::min<int64_t>(tiles * n_tiles, at::cuda::getCurrentDeviceProperties()->multiProcessorCount));
+    TORCH_CHECK(stat_partials->numel() >= groups * 8 * p.n_total, "stat_partials too small: need ", groups * 8 * p.n_total);
     TORCH_CHECK(split_k <= 1, "statistics need the full reduction in one CTA");
   }
   if (persistent && split_k <= 1) return ddpt::launch_conv_gemm_persistent(p, (int)block_n, current_stream());
@@ -189,7 +192,34 @@ void wgrad_gemm(at::Tensor dy, at::Tensor x, at::Tensor dw, std::vector<int64_t>
 
 }  // namespace
 
+namespace ddpt {
+struct UmmaProbeArgs {
+  int a_rows, a_blocks, b_rows, b_blocks;
+  int a_start_off, a_lbo, a_sbo, a_base_offset, a_mn_major, a_kstep_bytes;
+  int b_start_off, b_lbo, b_sbo, b_base_offset, b_mn_major, b_kstep_bytes;
+  int ksteps;
+  float* out;
+};
+void launch_umma_probe(const void* a, int a_ld, int a_total_rows, const void* b, int b_ld, int b_total_rows,
+                       const UmmaProbeArgs& p, cudaStream_t stream);
+}  // namespace ddpt
+
+// a: [rows, a_ld] bf16, b: [rows, b_ld] bf16; cfg = 17 ints in UmmaProbeArgs order.  Returns D [128, 64] fp32.
+static at::Tensor umma_probe(at::Tensor a, at::Tensor b, std::vector<int64_t> cfg) {
+  TORCH_CHECK(cfg.size() == 17 && a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && a.is_contiguous() && b.is_contiguous());
+  c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor out = at::zeros({128, 64}, a.options().dtype(at::kFloat));
+  ddpt::UmmaProbeArgs p{(int)cfg[0], (int)cfg[1], (int)cfg[2], (int)cfg[3], (int)cfg[4], (int)cfg[5], (int)cfg[6],
+                        (int)cfg[7], (int)cfg[8], (int)cfg[9], (int)cfg[10], (int)cfg[11], (int)cfg[12], (int)cfg[13],
+                        (int)cfg[14], (int)cfg[15], (int)cfg[16], out.data_ptr<float>()};
+  ddpt::launch_umma_probe(a.data_ptr(), (int)a.size(1), (int)a.size(0), b.data_ptr(), (int)b.size(1), (int)b.size(0), p,
+                          at::cuda::getCurrentCUDAStream().stream());
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("umma_probe", &umma_probe);
   m.doc() = "ddpt_b200 sm_100a kernels";
   m.def("multi_tensor_scale", &multi_tensor_scale);
   m.def("multi_tensor_axpby", &multi_tensor_axpby);

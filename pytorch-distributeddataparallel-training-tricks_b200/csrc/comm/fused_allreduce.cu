@@ -147,25 +147,61 @@ fused_allreduce_kernel(AllReduceArgs a) {
   const long long slice = a.numel / a.world;              // elements owned by this rank
   const long long nvec = slice >> 2;
   const long long base = a.offset + (long long)a.rank * slice;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-    float4 acc;
+  // kUnroll independent 16-byte vectors per thread are in flight at once: NVLink round trips are ~2 us, so
+  // bandwidth is bytes-in-flight limited (blocks x 512 threads x kUnroll x 16 B x world loads).
+  constexpr int kUnroll = 8;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < nvec; i0 += stride * kUnroll) {
+    float4 acc[kUnroll];
     if (ALGO == kAlgoMultimem) {
-      acc = mc_ld_reduce_f4(a.mc_buf + base + 4 * i);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < nvec) acc[u] = mc_ld_reduce_f4(a.mc_buf + base + 4 * i);
+      }
     } else {
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
       for (int r = 0; r < a.world; ++r) {
-        const float4 v = ld_f4(a.peer_bufs[(a.rank + r) % a.world] + base + 4 * i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const float* src = a.peer_bufs[(a.rank + r) % a.world] + base;
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec) v[u] = ld_f4(src + 4 * i);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (i0 + u * stride < nvec) {
+            acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+          }
+        }
       }
     }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    bad |= !finite4(acc);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (i0 + u * stride < nvec) {
+        acc[u].x *= scale; acc[u].y *= scale; acc[u].z *= scale; acc[u].w *= scale;
+        bad |= !finite4(acc[u]);
+      }
+    }
     if (ALGO == kAlgoMultimem) {
-      mc_st_f4(a.mc_buf + base + 4 * i, acc);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < nvec) mc_st_f4(a.mc_buf + base + 4 * i, acc[u]);
+      }
     } else {
 #pragma unroll 1
-      for (int r = 0; r < a.world; ++r) st_f4(a.peer_bufs[(a.rank + r) % a.world] + base + 4 * i, acc);
+      for (int r = 0; r < a.world; ++r) {
+        float* dst = a.peer_bufs[(a.rank + r) % a.world] + base;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec) st_f4(dst + 4 * i, acc[u]);
+        }
+      }
     }
   }
   publish_overflow(a, bad);
@@ -212,7 +248,7 @@ void launch_fused_allreduce(const AllReduceArgs& args, cudaStream_t stream) {
   } else {
     const long long vec_per_rank = (args.numel / args.world) >> 2;
     long long want = (vec_per_rank + kThreads - 1) / kThreads;
-    blocks = args.blocks > 0 ? args.blocks : 24;
+    blocks = args.blocks > 0 ? args.blocks : 32;
     if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
     if (want < blocks) blocks = (int)(want > 0 ? want : 1);
     if (algo == kAlgoMultimem) fused_allreduce_kernel<kAlgoMultimem><<<blocks, kThreads, 0, stream>>>(a);

@@ -59,6 +59,15 @@ def _block_n(n_total: int, prefer: Optional[int]) -> int:
     raise ValueError(f"N={n_total} is not a multiple of 64")
 
 
+def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Optional[int] = None,
+                    device=None) -> int:
+    """Row groups (x4 rows x 2 x C floats) a conv epilogue may write into ``stat_partials``."""
+    bn_, bh, bw = pick_box(out_n, out_h, out_w)
+    tiles_m = -(-out_w // bw) * -(-out_h // bh) * -(-out_n // bn_)
+    sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    return max(tiles_m, min(tiles_m * (c_out // _block_n(c_out, block_n)), sms))
+
+
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,

@@ -47,11 +47,10 @@ class _Workspace:
         self.bcoef = [torch.zeros(3, c, dtype=f32, device=device) for c in (64, 128, 256, 512, 512)]
         self.logits = e(batch, 10, dt=f32)
         # statistic partial rows: conv epilogues write 4 rows (warp quadrants) per M tile
-        def tiles(n, h, w):
-            bn_, bh, bw = gemm.pick_box(n, h, w)
-            return -(-w // bw) * -(-h // bh) * -(-n // bn_)
-        rows = [ext.conv0_partial_rows(), 4 * tiles(batch, 24, 24), 4 * tiles(batch, 10, 10),
-                4 * tiles(batch, 8, 8), 4 * tiles(1, 1, batch)]
+        groups = gemm.stat_row_groups
+        rows = [ext.conv0_partial_rows(), 4 * groups(batch, 24, 24, 128, None, device),
+                4 * groups(batch, 10, 10, 256, None, device), 4 * groups(batch, 8, 8, 512, None, device),
+                4 * groups(1, 1, batch, 512, 64, device)]
         chans = (64, 128, 256, 512, 512)
         self.part = torch.zeros(max(max(r * 2 * c for r, c in zip(rows, chans)),
                                     ext.bn_bwd_partial_rows() * 2 * 512), dtype=f32, device=device)

@@ -58,3 +58,23 @@ def test_idx_reader_on_reference_dataset(reference_root):
 def test_missing_dataset_message(tmp_path):
     with pytest.raises(FileNotFoundError, match="--synthetic"):
         load_mnist(str(tmp_path))
+
+
+def test_native_threaded_loader_matches_indexing():
+    """csrc/data/host_loader.cpp: threaded gather into rotating buffers (pinned on CUDA boxes)."""
+    from ddpt_b200 import ops
+    if ops.load_ext() is None:
+        pytest.skip("extension not built")
+    from ddpt_b200.ops.host_loader import PinnedGatherLoader
+    data = synthetic_mnist(3000, seed=4)
+    loader = PinnedGatherLoader(data.images, data.labels, 256, None, depth=4, threads=3)
+    sampler = ShardedSampler(3000, 2, 1)
+    for epoch in range(3):
+        sampler.set_epoch(epoch)
+        idx = sampler.indices()
+        nb = -(-len(idx) // 256)
+        imgs, lbls, sizes = [], [], []
+        for img, lbl, nbytes in loader.epoch(idx, nb):
+            imgs.append(img.clone()); lbls.append(lbl.clone()); sizes.append(img.shape[0])
+        assert sizes == [256] * (nb - 1) + [len(idx) - 256 * (nb - 1)]
+        assert torch.equal(torch.cat(imgs)[:, 0], data.images[idx]) and torch.equal(torch.cat(lbls), data.labels[idx])

@@ -89,10 +89,12 @@ def test_conv3x3_fwd_and_stats(ext, n, h, w, ci, co):
     want = _conv_ref(x, wk, co, ci) + bias.view(1, -1, 1, 1)
     y32, tiles = gemm.conv_fwd(x, wk, 3, 3, bias, out_dtype=torch.float32)
     assert _rel_err(y32.permute(0, 3, 1, 2), want) < 2e-3
-    stats = torch.zeros(tiles * 8 * co, device="cuda")
+    groups = gemm.stat_row_groups(n, h - 2, w - 2, co)
+    assert groups >= tiles
+    stats = torch.zeros(groups * 8 * co, device="cuda")
     y, _ = gemm.conv_fwd(x, wk, 3, 3, bias, stat_partials=stats)
     assert _rel_err(y.permute(0, 3, 1, 2), want) < 1e-2
-    part = stats.view(tiles * 4, 2, co).sum(0)
+    part = stats.view(groups * 4, 2, co).sum(0)
     flat = want.permute(0, 2, 3, 1).reshape(-1, co)
     torch.testing.assert_close(part[0], flat.sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(flat.shape[0]))
     torch.testing.assert_close(part[1], (flat * flat).sum(0), rtol=2e-3, atol=1e-2)

@@ -73,7 +73,7 @@ def _allreduce_vs_nccl(rank, world, provider):
     ext = require_native()
     dev = torch.device("cuda", rank)
     n = 64 * 1024 * 1024 // 4
-    region = SymmetricRegion(n, dev)
+    region = SymmetricRegion(n + 1024, dev)
     info = {"provider": region.provider, "multicast": region.mc_ptr != 0}
     state = torch.tensor([8.0, 0.125, 0.0, 0.0, 0.0], device=dev)
     algos = [1, 2] + ([3] if region.mc_ptr else [])
