@@ -59,8 +59,11 @@ def main():
                         rows.append(dict(op=f"{name}.dgrad{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                 if ci % bn == 0:
                     dw = torch.zeros(co, 3, 3, ci, device="cuda")
-                    t = timeit(lambda: gemm.conv_wgrad(dy, x, 3, 3, out=dw, block_n=bn), flush=flush)
-                    rows.append(dict(op=f"{name}.wgrad", block_n=bn, ms=t, tflops=flops / t / 1e9))
+                    for mt in (False, True):
+                        t = timeit(lambda: gemm.conv_wgrad(dy, x, 3, 3, out=dw, block_n=bn, accumulate=True, multitap=mt),
+                                   flush=flush)
+                        rows.append(dict(op=f"{name}.wgrad{'.multitap' if mt else ''}", block_n=bn, ms=t,
+                                         tflops=flops / t / 1e9))
             # library reference for the same layer (channels_last bf16)
             xn = x.permute(0, 3, 1, 2)
             wn = wk.view(co, 3, 3, ci).permute(0, 3, 1, 2)

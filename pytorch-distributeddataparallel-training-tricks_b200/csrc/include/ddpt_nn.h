@@ -60,5 +60,8 @@ struct WgradProblem {
   int accumulate;                          // 1: add into dw even when split_k == 1 (beta = 1)
 };
 void launch_wgrad_gemm(const WgradProblem& p, int block_n, cudaStream_t stream);
+// Halo-reuse variant: one CTA accumulates a group of filter taps from a single dY + X(halo) brick load.
+// box_w must be a multiple of 8; the output is always accumulated (red.add) into dw.
+void launch_wgrad_gemm_multitap(const WgradProblem& p, int block_n, cudaStream_t stream);
 
 }  // namespace ddpt

@@ -181,17 +181,19 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
 // BatchNorm forward
 // ================================================================================================
 // One block per 32 channels; 8 row-groups of 32 lanes walk the partial rows (coalesced across channels).
-__global__ void __launch_bounds__(kThreads)
+constexpr int kFinGroups = 32;                       // row groups per block in the *_finalize kernels
+
+__global__ void __launch_bounds__(32 * kFinGroups)
 bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    BnCoeffs out, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ nbt) {
-  __shared__ double s_sum[8][32], s_sq[8][32];
+  __shared__ double s_sum[kFinGroups][32], s_sq[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double sum = 0.0, sq = 0.0;
   if (c < channels) {
-    for (int p = grp; p < num_partials; p += 8) {
+    for (int p = grp; p < num_partials; p += kFinGroups) {
       sum += (double)partials[((size_t)p * 2) * channels + c];
       sq += (double)partials[((size_t)p * 2 + 1) * channels + c];
     }
@@ -200,7 +202,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
   s_sq[grp][lane] = sq;
   __syncthreads();
   if (grp == 0 && c < channels) {
-    for (int g = 1; g < 8; ++g) { sum += s_sum[g][lane]; sq += s_sq[g][lane]; }
+    for (int g = 1; g < kFinGroups; ++g) { sum += s_sum[g][lane]; sq += s_sq[g][lane]; }
     const double mean = sum / count;
     double var = sq / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -321,7 +323,7 @@ __device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, i
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
   extern __shared__ float s_part[];                       // [2][c]
   const int cv = k.c >> 3;
@@ -415,17 +417,17 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
   for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) partials[(size_t)blockIdx.x * 2 * k.c + i] = s_part[i];
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(32 * kFinGroups)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                        int accumulate) {
-  __shared__ double s_a[8][32], s_b[8][32];
+  __shared__ double s_a[kFinGroups][32], s_b[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double a = 0.0, b = 0.0;
   if (c < channels) {
-    for (int p = grp; p < num_partials; p += 8) {
+    for (int p = grp; p < num_partials; p += kFinGroups) {
       a += (double)partials[((size_t)p * 2) * channels + c];
       b += (double)partials[((size_t)p * 2 + 1) * channels + c];
     }
@@ -434,7 +436,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
   s_b[grp][lane] = b;
   __syncthreads();
   if (grp == 0 && c < channels) {
-    for (int g = 1; g < 8; ++g) { a += s_a[g][lane]; b += s_b[g][lane]; }
+    for (int g = 1; g < kFinGroups; ++g) { a += s_a[g][lane]; b += s_b[g][lane]; }
     if (accumulate) { dbeta[c] += (float)a; dgamma[c] += (float)b; }
     else { dbeta[c] = (float)a; dgamma[c] = (float)b; }
     coef[c] = gamma[c] * invstd[c];
@@ -444,7 +446,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                     float* __restrict__ dbias) {
   extern __shared__ float s_db[];                          // [c]
@@ -672,7 +674,7 @@ void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, flo
 void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                         const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
                         float* running_var, long long* nbt, cudaStream_t s) {
-  bn_finalize_kernel<<<(channels + 31) / 32, kThreads, 0, s>>>(partials, num_partials, channels, count, gamma, beta,
+  bn_finalize_kernel<<<(channels + 31) / 32, 32 * kFinGroups, 0, s>>>(partials, num_partials, channels, count, gamma, beta,
                                                                 eps, momentum, out, running_mean, running_var, nbt);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -729,7 +731,7 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                             const float* invstd, float* dgamma, float* dbeta, float* coef, int accumulate,
                             cudaStream_t s) {
-  bn_bwd_finalize_kernel<<<(channels + 31) / 32, kThreads, 0, s>>>(partials, num_partials, channels, count, gamma,
+  bn_bwd_finalize_kernel<<<(channels + 31) / 32, 32 * kFinGroups, 0, s>>>(partials, num_partials, channels, count, gamma,
                                                                     invstd, dgamma, dbeta, coef, accumulate);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }

@@ -1,0 +1,277 @@
+// Multi-tap weight-gradient GEMM for sm_100a (tcgen05 + TMEM + TMA): halo reuse of the activation brick.
+//
+//   dW[m, tap, c] = sum over output pixels p:  dY[p, m] * X[p + tap, c]
+//
+// wgrad_gemm.cu gives every filter tap its own CTA, so the dY brick is fetched 9 times and a shifted X brick
+// once per tap -- the kernel is L2-bandwidth bound (24 KiB per 128 MMA cycles for C_in = 64).  Here one CTA
+// owns a *group* of taps (as many as fit TMEM: taps x BLOCK_N <= 512 columns).  Per reduction brick it loads
+//   - the dY brick once                       [K = brick pixels][128 channels]   (MN-major A)
+//   - the X brick once, including its halo    [(bh + nr - 1) x bn x (bw + ns - 1) pixels][BLOCK_N channels]
+// and issues one MMA chain per tap whose B descriptor is a *shifted view* of the halo tile: the start address
+// moves by whole 128-byte rows and the 8-row K groups are (bw + ns - 1) * 128 bytes apart.  That is legal
+// because the tensor core applies the 128B swizzle to absolute shared-memory addresses, exactly like TMA
+// (measured: profiles/umma_descriptor_probe.txt), so no copy or re-layout is needed.
+// L2 traffic per MMA cycle drops ~5x for Toy_Net's conv.3 and the kernel becomes tensor-core bound.
+#include <cuda.h>
+#include <stdexcept>
+#include "../include/ddpt_nn.h"
+#include "../include/ddpt_common.cuh"
+#include "../include/umma.cuh"
+#include "tensor_map.h"
+
+namespace ddpt {
+namespace {
+
+using namespace umma;
+
+constexpr int kBlockM = 128;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kMaxGroups = 9;
+
+struct TapGroup {
+  int r0, nr, s0, ns;          // filter rows [r0, r0+nr) x columns [s0, s0+ns)
+  int map;                     // which X tensor map (box shape) this group uses
+  int halo_rows;               // (bh + nr - 1) * bn * (bw + ns - 1)
+};
+
+struct MtArgs {
+  int tiles_w, tiles_h, tiles_n;
+  int box_w, box_h, box_n, brick_rows;
+  int taps_w, num_taps;
+  int c_total;
+  int stages, slot_a, slot_x;
+  int num_groups;
+  TapGroup groups[kMaxGroups];
+  float* dw;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int TMEM_COLS>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x0,
+                      const __grid_constant__ CUtensorMap tmap_x1, const MtArgs args) {
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, true, true);
+  constexpr int kABlocks = kBlockM / 64, kBBlocks = BN / 64;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABlocks * args.slot_a + kBBlocks * args.slot_x;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + args.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + args.stages;
+  uint64_t* accum_bar = empty_bar + args.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int gidx = blockIdx.y % args.num_groups;
+  const int c0 = (blockIdx.y / args.num_groups) * BN;
+  const TapGroup grp = args.groups[gidx];
+  const int group_taps = grp.nr * grp.ns;
+
+  const int total_bricks = args.tiles_w * args.tiles_h * args.tiles_n;
+  const int per_split = (total_bricks + gridDim.z - 1) / gridDim.z;
+  const int brick_begin = blockIdx.z * per_split;
+  const int num_bricks = max(min(total_bricks, brick_begin + per_split) - brick_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(grp.map == 0 ? &tmap_x0 : &tmap_x1);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: dY brick + X halo brick per reduction step =====
+    if (lane == 0) {
+      const CUtensorMap* tmx = grp.map == 0 ? &tmap_x0 : &tmap_x1;
+      const uint32_t tx_bytes = (kABlocks * args.brick_rows + kBBlocks * grp.halo_rows) * 128;
+      for (int i = 0; i < num_bricks; ++i) {
+        const int s = i % args.stages;
+        const uint32_t phase = (i / args.stages) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1, 31);
+        const int brick = brick_begin + i;
+        const int bw = brick % args.tiles_w;
+        const int bh = (brick / args.tiles_w) % args.tiles_h;
+        const int bn = brick / (args.tiles_w * args.tiles_h);
+        const int w0 = bw * args.box_w, h0 = bh * args.box_h, n0 = bn * args.box_n;
+        uint8_t* stage = smem + s * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        // tensor maps are declared (C, W, N, H): the brick's pixel order in shared memory is w, then n, then h
+#pragma unroll
+        for (int j = 0; j < kABlocks; ++j)
+          tma_load_4d(stage + j * args.slot_a, &tmap_dy, &full_bar[s], m0 + j * 64, w0, n0, h0);
+#pragma unroll
+        for (int j = 0; j < kBBlocks; ++j)
+          tma_load_4d(stage + kABlocks * args.slot_a + j * args.slot_x, tmx, &full_bar[s], c0 + j * 64, w0 + grp.s0,
+                      n0, h0 + grp.r0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one chain per tap, B = shifted view of the halo tile =====
+    if (lane == 0) {
+      const int k_steps = args.brick_rows / kUmmaK;
+      const int gpr = args.box_w / 8;                      // 8-pixel K groups per (h, n) row of the brick
+      const int xw = args.box_w + grp.ns - 1;              // halo row width in pixels
+      const uint32_t sbo_x = gpr == 1 ? xw * 128 : 1024;
+      for (int i = 0; i < num_bricks; ++i) {
+        const int s = i % args.stages;
+        const uint32_t phase = (i / args.stages) & 1;
+        mbar_wait(&full_bar[s], phase, 32);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t x_addr = a_addr + kABlocks * args.slot_a;
+        for (int t = 0; t < group_taps; ++t) {
+          const int dr = t / grp.ns, ds = t - dr * grp.ns;
+          for (int k = 0; k < k_steps; ++k) {
+            const int g0 = 2 * k;                           // first of the two 8-pixel K groups of this step
+            const int row = g0 / gpr, cg = g0 - row * gpr;  // (h, n) row of the brick, 8-pixel column group
+            const uint32_t x_off = ((row + dr * args.box_n) * xw + cg * 8 + ds) * 128;
+            const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
+            const uint64_t bdesc = make_smem_desc(x_addr + x_off, args.slot_x, sbo_x);
+            mma_bf16_ss(tmem_base + t * BN, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(accum_bar);
+    }
+  } else {
+    // ===== epilogue: red.add every tap's 128 x BN accumulator into dW[m, tap, c] =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(accum_bar, 0, 33);
+    tc_fence_after();
+    for (int t = 0; t < group_taps; ++t) {
+      const int dr = t / grp.ns, ds = t - dr * grp.ns;
+      const int tap = (grp.r0 + dr) * args.taps_w + grp.s0 + ds;
+      float* out_row = args.dw + (static_cast<long long>(m0 + row) * args.num_taps + tap) * args.c_total + c0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + t * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        if (num_bricks > 0) {
+          float* o = out_row + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <int BN>
+void launch_impl(const WgradProblem& p, cudaStream_t stream) {
+  MtArgs a{};
+  a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
+  a.brick_rows = p.box_w * p.box_h * p.box_n;
+  a.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;
+  a.tiles_h = (p.out_h + p.box_h - 1) / p.box_h;
+  a.tiles_n = (p.out_n + p.box_n - 1) / p.box_n;
+  a.taps_w = p.taps_w; a.num_taps = p.taps_h * p.taps_w;
+  a.c_total = p.c_total; a.dw = p.dw;
+  const int gpr = p.box_w / 8;
+  if (p.box_w % 8 != 0 || (gpr != 1 && gpr % 2 != 0) || a.brick_rows % kUmmaK != 0 || a.brick_rows > 128 ||
+      p.m_total % kBlockM != 0 || p.c_total % BN != 0)
+    throw std::runtime_error("wgrad_multitap: need box_w % 8 == 0 (1 or an even number of 8-pixel groups), "
+                             "brick % 16 == 0, brick <= 128, M % 128 == 0, C % BLOCK_N == 0");
+  // tap groups: as many taps per CTA as fit 512 TMEM columns, cut along filter rows / columns
+  const int max_taps = 512 / BN;
+  int rows_per_group = 1, cols_per_group = p.taps_w;
+  if (max_taps >= p.taps_w) rows_per_group = std::min(p.taps_h, max_taps / p.taps_w);
+  else cols_per_group = max_taps;
+  int max_group_taps = 0, max_halo = 0;
+  uint32_t shapes[2][2] = {{0, 0}, {0, 0}};
+  int num_shapes = 0;
+  for (int r0 = 0; r0 < p.taps_h; r0 += rows_per_group)
+    for (int s0 = 0; s0 < p.taps_w; s0 += cols_per_group) {
+      TapGroup g{};
+      g.r0 = r0; g.nr = std::min(rows_per_group, p.taps_h - r0);
+      g.s0 = s0; g.ns = std::min(cols_per_group, p.taps_w - s0);
+      g.halo_rows = (p.box_h + g.nr - 1) * p.box_n * (p.box_w + g.ns - 1);
+      g.map = -1;
+      for (int k = 0; k < num_shapes; ++k)
+        if (shapes[k][0] == (uint32_t)g.nr && shapes[k][1] == (uint32_t)g.ns) g.map = k;
+      if (g.map < 0) {
+        if (num_shapes == 2) throw std::runtime_error("wgrad_multitap: more than two halo shapes");
+        shapes[num_shapes][0] = g.nr; shapes[num_shapes][1] = g.ns;
+        g.map = num_shapes++;
+      }
+      if (a.num_groups == kMaxGroups) throw std::runtime_error("wgrad_multitap: too many tap groups");
+      a.groups[a.num_groups++] = g;
+      max_group_taps = std::max(max_group_taps, g.nr * g.ns);
+      max_halo = std::max(max_halo, g.halo_rows);
+    }
+  if (max_halo > 256) throw std::runtime_error("wgrad_multitap: halo brick exceeds a 256-row TMA box");
+  a.slot_a = round_up(a.brick_rows * 128, 1024);
+  a.slot_x = round_up(max_halo * 128, 1024);
+  const int stage_bytes = (kBlockM / 64) * a.slot_a + (BN / 64) * a.slot_x;
+  a.stages = std::min(8, (kMaxSmem - 2048) / stage_bytes);
+  if (a.stages < 2) throw std::runtime_error("wgrad_multitap: stage does not fit shared memory twice");
+  const size_t smem_bytes = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16;
+
+  // (C, W, N, H) dimension order => bricks land in shared memory as [h][n][w] rows of 64 channels
+  auto make_map = [&](const void* base, int c, int w, int h, int n, int bw, int bh, int bn) {
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)n, (uint64_t)h};
+    const uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)c * w * h * 2, (uint64_t)c * w * 2};
+    const uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bn, (uint32_t)bh};
+    return make_tensor_map_bf16(base, 4, dims, strides, box);
+  };
+  CUtensorMap tmap_dy = make_map(p.dy, p.m_total, p.out_w, p.out_h, p.out_n, p.box_w, p.box_h, p.box_n);
+  CUtensorMap tmap_x[2];
+  for (int k = 0; k < 2; ++k) {
+    const int kk = k < num_shapes ? k : 0;
+    tmap_x[k] = make_map(p.x, p.c_total, p.in_w, p.in_h, p.out_n, p.box_w + (int)shapes[kk][1] - 1,
+                         p.box_h + (int)shapes[kk][0] - 1, p.box_n);
+  }
+  dim3 grid(p.m_total / kBlockM, a.num_groups * (p.c_total / BN), p.split_k > 1 ? p.split_k : 1);
+  const int cols = max_group_taps * BN;
+  auto run = [&](auto kernel) {
+    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_dy, tmap_x[0], tmap_x[1], a);
+  };
+  if (cols <= 64) run(wgrad_multitap_kernel<BN, 64>);
+  else if (cols <= 128) run(wgrad_multitap_kernel<BN, 128>);
+  else if (cols <= 256) run(wgrad_multitap_kernel<BN, 256>);
+  else run(wgrad_multitap_kernel<BN, 512>);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+// Same contract as launch_wgrad_gemm, except that the output is always accumulated (red.add): the caller
+// provides a zero-initialised (or beta = 1) dW.
+void launch_wgrad_gemm_multitap(const WgradProblem& p, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_impl<64>(p, stream);
+    case 128: return launch_impl<128>(p, stream);
+    case 256: return launch_impl<256>(p, stream);
+  }
+  throw std::runtime_error("wgrad_multitap: block_n must be 64, 128 or 256");
+}
+
+}  // namespace ddpt

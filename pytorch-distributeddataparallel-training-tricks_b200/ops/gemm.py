@@ -100,24 +100,63 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
     return out
 
 
+@functools.lru_cache(maxsize=None)
+def pick_box_multitap(out_n: int, out_h: int, out_w: int, max_rows: int = 128) -> Tuple[int, int, int]:
+    """Reduction brick for the halo-reuse wgrad kernel: width a multiple of 8 (one or an even number of
+    8-pixel K groups per row), rows a multiple of 16 and <= max_rows, fewest wasted rows."""
+    widths = [8] + [w for w in (16, 32, 64, 128) if w <= max_rows and w <= max(out_w, 8)]
+    best, best_key = None, None
+    total = out_n * out_h * out_w
+    for bw in widths:
+        for bh in range(1, min(out_h, max_rows // bw) + 1):
+            for bn in range(1, min(out_n, max_rows // (bw * bh)) + 1):
+                rows = bw * bh * bn
+                if rows % 16:
+                    continue
+                bricks = -(-out_w // bw) * -(-out_h // bh) * -(-out_n // bn)
+                # >= 64-row bricks first (pipeline granularity), then fewest wasted rows, then the tallest brick
+                # (smallest halo overhead for the multi-tap view)
+                key = (min(rows, 64), round(total / (bricks * rows), 3), bh, rows)
+                if best_key is None or key > best_key:
+                    best, best_key = (bn, bh, bw), key
+    if best is None:
+        raise ValueError(f"no multitap brick for {out_n}x{out_h}x{out_w}")
+    return best
+
+
+def use_multitap(flag: Optional[bool] = None) -> bool:
+    """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu); DDPT_WGRAD_MULTITAP=0 disables."""
+    if flag is not None:
+        return flag
+    return os.environ.get("DDPT_WGRAD_MULTITAP", "1") != "0"
+
+
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
-               split_k: Optional[int] = None, accumulate: bool = False, block_n: Optional[int] = None):
+               split_k: Optional[int] = None, accumulate: bool = False, block_n: Optional[int] = None,
+               multitap: Optional[bool] = None):
     """dW [C_out, kh, kw, C_in] fp32 = sum over pixels dy[p, :]^T x[p + tap, :]."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
     c_in = x.shape[3]
-    box = pick_box(n, ho, wo, 16)
     bn = _block_n(c_in, block_n)
+    mt = use_multitap(multitap)
+    if mt:
+        box = pick_box_multitap(n, ho, wo, 128 if bn <= 128 else 64)
+        max_taps = 512 // bn
+        groups = (-(-kh // max(1, min(kh, max_taps // kw)))) if max_taps >= kw else kh * -(-kw // max_taps)
+        ctas = (c_out // 128) * groups * (c_in // bn)
+    else:
+        box = pick_box(n, ho, wo, 16)
+        ctas = (c_out // 128) * kh * kw * (c_in // bn)
     if split_k is None:
         bricks = -(-wo // box[2]) * -(-ho // box[1]) * -(-n // box[0])
-        ctas = (c_out // 128) * kh * kw * (c_in // bn)
         sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
         split_k = max(1, min(bricks, -(-2 * sms // ctas)))
     if out is None:
         out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
-    elif split_k > 1 and not accumulate:
+    elif not accumulate and (split_k > 1 or mt):
         out.zero_()
-    ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn)
+    ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn, mt)
     return out
 
 
@@ -139,10 +178,10 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = Non
 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
-                 split_k: Optional[int] = None, accumulate: bool = False):
+                 split_k: Optional[int] = None, accumulate: bool = False, multitap: Optional[bool] = None):
     """dw [N, K] fp32 = dy [M, N]^T @ x [M, K]."""
     m, n = dy.shape
     k = x.shape[1]
     res = conv_wgrad(dy.view(1, 1, m, n), x.view(1, 1, m, k), 1, 1,
-                     None if out is None else out.view(n, 1, 1, k), split_k, accumulate)
+                     None if out is None else out.view(n, 1, 1, k), split_k, accumulate, None, multitap)
     return res.view(n, k)

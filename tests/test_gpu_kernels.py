@@ -69,8 +69,9 @@ def test_linear_wgrad_mn_major_both(ext, m, n, k):
     dy, x = _bf16(m, n, seed=7), _bf16(m, k, seed=8)
     want = dy.float().t() @ x.float()
     for split in (1, None):
-        dw = gemm.linear_wgrad(dy, x, split_k=split)
-        assert _rel_err(dw, want) < 2e-3, split
+        for mt in (False, True):
+            dw = gemm.linear_wgrad(dy, x, split_k=split, multitap=mt)
+            assert _rel_err(dw, want) < 2e-3, (split, mt)
 
 
 CONVS = [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512), (5, 7, 9, 64, 64)]
@@ -111,7 +112,8 @@ def test_conv3x3_dgrad(ext, n, h, w, ci, co):
     assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
 
 
-@pytest.mark.parametrize("n,h,w,ci,co", [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512)])
+@pytest.mark.parametrize("n,h,w,ci,co", [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512),
+                                         (3, 9, 13, 64, 128)])
 def test_conv3x3_wgrad(ext, n, h, w, ci, co):
     from ddpt_b200.ops import gemm
     dy, x = _bf16(n, h - 2, w - 2, co, seed=13), _bf16(n, h, w, ci, seed=14)
@@ -120,8 +122,9 @@ def test_conv3x3_wgrad(ext, n, h, w, ci, co):
     F.conv2d(xg, wref).backward(dy.float().permute(0, 3, 1, 2))
     want = wref.grad.permute(0, 2, 3, 1)                       # [co, kh, kw, ci]
     for split in (1, None):
-        dw = gemm.conv_wgrad(dy, x, 3, 3, split_k=split)
-        assert _rel_err(dw, want) < 2e-3, split
+        for mt in (False, True):
+            dw = gemm.conv_wgrad(dy, x, 3, 3, split_k=split, multitap=mt)
+            assert _rel_err(dw, want) < 2e-3, (split, mt)
 
 
 def test_toy_net_tail_batch_sizes(ext):
