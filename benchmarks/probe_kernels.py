@@ -49,13 +49,12 @@ def main():
             dy = torch.randn(B, h - 2, w - 2, co, device="cuda").bfloat16()
             flops = 2.0 * B * (h - 2) * (w - 2) * co * ci * 9
             for bn in (64, 128, 256):
-                for pers in (False, True):
-                    tag = ".persist" if pers else ""
+                for pers, halo, tag in ((False, False, ""), (True, False, ".persist"), (True, True, ".halo")):
                     if co % bn == 0:
-                        t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn, persistent=pers), flush=flush)
+                        t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn, persistent=pers, halo=halo), flush=flush)
                         rows.append(dict(op=f"{name}.fwd{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                     if ci % bn == 0:
-                        t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn, persistent=pers), flush=flush)
+                        t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn, persistent=pers, halo=halo), flush=flush)
                         rows.append(dict(op=f"{name}.dgrad{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                 if ci % bn == 0:
                     dw = torch.zeros(co, 3, 3, ci, device="cuda")

@@ -127,7 +127,7 @@ void cast_bf16(at::Tensor src, at::Tensor dst) {
 int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_t> out_nhw,
                   std::vector<int64_t> box_nhw, std::vector<int64_t> taps_hw, int64_t tap_sign,
                   std::vector<int64_t> a_off_hw, bool b_mn_major, c10::optional<at::Tensor> bias, bool relu,
-                  c10::optional<at::Tensor> stat_partials, int64_t split_k, int64_t block_n, bool persistent) {
+                  c10::optional<at::Tensor> stat_partials, int64_t split_k, int64_t block_n, int64_t mode) {
   check_cuda(a, "a", at::kBFloat16); check_cuda(b, "b", at::kBFloat16);
   TORCH_CHECK(a.dim() == 4 && a.is_contiguous(), "a must be contiguous [N,H,W,C]");
   TORCH_CHECK(b.dim() == 2 && b.stride(1) == 1, "b must be 2-D with unit inner stride");
@@ -166,7 +166,9 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
     TORCH_CHECK(stat_partials->numel() >= groups * 8 * p.n_total, "stat_partials too small: need ", groups * 8 * p.n_total);
     TORCH_CHECK(split_k <= 1, "statistics need the full reduction in one CTA");
   }
-  if (persistent && split_k <= 1) return ddpt::launch_conv_gemm_persistent(p, (int)block_n, current_stream());
+  // mode: 0 = one CTA per tile (split-K capable), 1 = persistent, 2 = persistent + halo reuse
+  if (mode == 2 && split_k <= 1) return ddpt::launch_conv_gemm_halo(p, (int)block_n, current_stream());
+  if (mode >= 1 && split_k <= 1) return ddpt::launch_conv_gemm_persistent(p, (int)block_n, current_stream());
   return ddpt::launch_conv_gemm(p, (int)block_n, current_stream());
 }
 

@@ -45,6 +45,9 @@ int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream)
 // Persistent variant (one CTA per SM, double-buffered TMEM accumulator); no split-K.  With stat_partials the
 // statistics are accumulated per CTA and the return value is the number of row groups written (= grid size).
 int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
+// Halo-reuse variant: the activation brick (+halo) is loaded once per channel chunk and every filter tap is a
+// shifted descriptor view; requires box_w == 8 and box_h * box_n <= 16.  Same return convention as persistent.
+int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
 
 // Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,
 // reduction over the pixel bricks; fp32 accumulate into a zero-initialised or beta=1 output).

@@ -1,0 +1,391 @@
+// Halo-reuse implicit-GEMM convolution (forward and data-gradient) for sm_100a: tcgen05 + TMEM + TMA.
+//
+// conv_gemm_persistent.cu streams one activation brick per (filter tap, 64-channel chunk): every input pixel
+// crosses L2->SM nine times and the layer is L2-bandwidth bound when C_in / C_out are small (Toy_Net conv.3).
+// Here the brick is loaded ONCE per channel chunk together with its halo,
+//     [(bh + kh - 1) rows][bn images][(8 + kw - 1) pixels][64 channels]     (TMA box over a (C, W, N, H) map)
+// and each of the kh*kw taps is a *descriptor view* into that tile: start address shifted by whole 128-byte
+// pixel rows, 8-pixel groups (8 + kw - 1) * 128 bytes apart.  tcgen05.mma swizzles on absolute shared-memory
+// addresses (profiles/umma_descriptor_probe.txt), so the views need no copy.  Weights either stay resident in
+// shared memory for the whole kernel (when all taps x chunks x BLOCK_N fit: conv.3) or stream through their
+// own ring.  Output tiles are 16 groups of 8 consecutive pixels ordered (h, n, w); everything else -- warp
+// roles, double-buffered TMEM accumulator, bias / ReLU / BatchNorm-statistics epilogue -- matches the
+// persistent kernel.
+#include <cuda.h>
+#include <stdexcept>
+#include "../include/ddpt_nn.h"
+#include "../include/ddpt_common.cuh"
+#include "../include/umma.cuh"
+#include "tensor_map.h"
+
+namespace ddpt {
+namespace {
+
+using namespace umma;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 320;
+constexpr int kEpilogueWarps = 8;
+constexpr int kMaxSmem = 227 * 1024;
+
+struct HaloArgs {
+  int tiles_w, tiles_h;
+  int box_h, box_n;                 // box_w is 8
+  int out_w, out_h, out_n;
+  int taps_w, taps_h, tap_sign;
+  int org_h_off, org_w_off;         // halo tile origin relative to the tile's (h0, w0)
+  int k_chunks, n_total;
+  int xw;                           // halo row width in pixels = 8 + taps_w - 1
+  int a_slot_bytes, a_tile_bytes;
+  int a_stages, b_stages;
+  long long ld_out;
+  void* out;
+  const float* bias;
+  float* stat_partials;
+  int relu, out_fp32;
+};
+
+template <int BN, bool B_MN, bool B_RES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const HaloArgs args, const int num_m_tiles, const int num_n_tiles) {
+  constexpr int kBStageBytes = BN * kBlockK * 2;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_taps = args.taps_h * args.taps_w;
+  const int total_kb = num_taps * args.k_chunks;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int b_slots = B_RES ? total_kb : args.b_stages;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + args.a_stages * args.a_slot_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + b_slots * kBStageBytes);
+  uint64_t* a_empty = a_full + args.a_stages;
+  uint64_t* b_full = a_empty + args.a_stages;
+  uint64_t* b_empty = b_full + args.b_stages;
+  uint64_t* tmem_full = b_empty + args.b_stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_ready = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 1);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < args.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < args.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpilogueWarps); }
+    mbar_init(b_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto load_b = [&](uint8_t* dst, uint64_t* bar, int tap, int chunk, int col0) {
+    if (!B_MN) {
+      tma_load_2d(dst, &tmap_b, bar, (tap * args.k_chunks + chunk) * kBlockK, col0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        tma_load_2d(dst + j * (kBlockK * 128), &tmap_b, bar, tap * args.n_total + col0 + j * 64, chunk * kBlockK);
+    }
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: one halo brick per (tile, channel chunk); weights resident or streamed per tap =====
+    if (lane == 0) {
+      if (B_RES) {
+        mbar_arrive_expect_tx(b_ready, static_cast<uint32_t>(total_kb) * kBStageBytes);
+        for (int tap = 0; tap < num_taps; ++tap)
+          for (int chunk = 0; chunk < args.k_chunks; ++chunk)
+            load_b(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes, b_ready, tap, chunk, 0);
+      }
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+        const int tw = tile_m % args.tiles_w;
+        const int th = (tile_m / args.tiles_w) % args.tiles_h;
+        const int tn = tile_m / (args.tiles_w * args.tiles_h);
+        const int w0 = tw * 8, h0 = th * args.box_h, n0 = tn * args.box_n;
+        for (int chunk = 0; chunk < args.k_chunks; ++chunk, ++ia) {
+          const int sa = ia % args.a_stages;
+          mbar_wait(&a_empty[sa], ((ia / args.a_stages) & 1) ^ 1, 41);
+          mbar_arrive_expect_tx(&a_full[sa], args.a_tile_bytes);
+          tma_load_4d(smem_a + sa * args.a_slot_bytes, &tmap_a, &a_full[sa], chunk * kBlockK, w0 + args.org_w_off, n0,
+                      h0 + args.org_h_off);
+          if (!B_RES) {
+            for (int tap = 0; tap < num_taps; ++tap, ++ib) {
+              const int sb = ib % args.b_stages;
+              mbar_wait(&b_empty[sb], ((ib / args.b_stages) & 1) ^ 1, 42);
+              mbar_arrive_expect_tx(&b_full[sb], kBStageBytes);
+              load_b(smem_b + sb * kBStageBytes, &b_full[sb], tap, chunk, tile_n * BN);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: every tap is a shifted view of the halo brick =====
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0, t = 0;
+      const uint32_t sbo_a = args.xw * 128;
+      if (B_RES) mbar_wait(b_ready, 0, 45);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 44);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int chunk = 0; chunk < args.k_chunks; ++chunk, ++ia) {
+          const int sa = ia % args.a_stages;
+          mbar_wait(&a_full[sa], (ia / args.a_stages) & 1, 43);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + sa * args.a_slot_bytes);
+          for (int tap = 0; tap < num_taps; ++tap) {
+            const int r = tap / args.taps_w, s = tap - r * args.taps_w;
+            const int dr = args.tap_sign > 0 ? r : args.taps_h - 1 - r;
+            const int ds = args.tap_sign > 0 ? s : args.taps_w - 1 - s;
+            uint32_t b_addr;
+            int sb = 0;
+            if (B_RES) {
+              b_addr = smem_u32(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes);
+            } else {
+              sb = ib % args.b_stages;
+              mbar_wait(&b_full[sb], (ib / args.b_stages) & 1, 46);
+              tc_fence_after();
+              b_addr = smem_u32(smem_b + sb * kBStageBytes);
+              ++ib;
+            }
+            const uint32_t a_view = a_addr + ((dr * args.box_n) * args.xw + ds) * 128;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = make_smem_desc(a_view + k * (kUmmaK * 2), 0, sbo_a);
+              const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
+                                          : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
+              mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+            }
+            if (!B_RES) mma_commit(&b_empty[sb]);
+          }
+          mma_commit(&a_empty[sa]);
+        }
+        mma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue: row m = group (h, n) x 8 pixels; quadrant = warp & 3, column half = (warp - 2) >> 2 =====
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int grp = row >> 3, dw = row & 7;
+    const int dh = grp / args.box_n, dn = grp - dh * args.box_n;
+    constexpr int kChunksPerWarp = (BN / 32) / 2;
+    float acc_s1[kChunksPerWarp], acc_s2[kChunksPerWarp];
+#pragma unroll
+    for (int cc = 0; cc < kChunksPerWarp; ++cc) acc_s1[cc] = acc_s2[cc] = 0.f;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+      const int tw = tile_m % args.tiles_w;
+      const int th = (tile_m / args.tiles_w) % args.tiles_h;
+      const int tn = tile_m / (args.tiles_w * args.tiles_h);
+      const int n = tn * args.box_n + dn, h = th * args.box_h + dh, w = tw * 8 + dw;
+      const bool valid = dh < args.box_h && n < args.out_n && h < args.out_h && w < args.out_w;
+      const long long out_row = (static_cast<long long>(n) * args.out_h + h) * args.out_w + w;
+      const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase, 47);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int c = half * kChunksPerWarp + cc;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const int col = tile_n * BN + c * 32;
+        if (args.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
+        }
+        if (args.stat_partials != nullptr) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s1[j] = valid ? f[j] : 0.f;
+            s2[j] = s1[j] * s1[j];
+          }
+#pragma unroll
+          for (int width = 16; width >= 1; width >>= 1) {
+            const bool upper = (lane & width) != 0;
+#pragma unroll
+            for (int j = 0; j < width; ++j) {
+              float keep1 = upper ? s1[j + width] : s1[j];
+              float give1 = upper ? s1[j] : s1[j + width];
+              float keep2 = upper ? s2[j + width] : s2[j];
+              float give2 = upper ? s2[j] : s2[j + width];
+              s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, give1, width);
+              s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, width);
+            }
+          }
+          acc_s1[cc] += s1[0];
+          acc_s2[cc] += s2[0];
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (args.out_fp32) {
+            float* o = static_cast<float*>(args.out) + out_row * args.ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(args.out) + out_row * args.ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(f[j], f[j + 1]);
+              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (args.stat_partials != nullptr) {
+      const int my_tile_n = blockIdx.x % num_n_tiles;
+      float* dst = args.stat_partials + (static_cast<long long>(blockIdx.x) * 4 + quad) * 2 * args.n_total;
+      for (int tn2 = 0; tn2 < num_n_tiles; ++tn2) {
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+          const int col = tn2 * BN + (half * kChunksPerWarp + cc) * 32 + lane;
+          dst[col] = tn2 == my_tile_n ? acc_s1[cc] : 0.f;
+          dst[args.n_total + col] = tn2 == my_tile_n ? acc_s2[cc] : 0.f;
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <int BN, bool B_MN>
+int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
+  constexpr int kBStageBytes = BN * kBlockK * 2;
+  if (p.box_w != 8 || p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_h * p.box_n > 16 || p.split_k > 1)
+    throw std::runtime_error("conv_gemm_halo: needs box_w == 8, box_h*box_n <= 16, C % 64 == 0, N % BLOCK_N == 0, no split-K");
+  HaloArgs a{};
+  a.box_h = p.box_h; a.box_n = p.box_n;
+  a.out_w = p.out_w; a.out_h = p.out_h; a.out_n = p.out_n;
+  a.tiles_w = (p.out_w + 7) / 8;
+  a.tiles_h = (p.out_h + p.box_h - 1) / p.box_h;
+  const int tiles_n = (p.out_n + p.box_n - 1) / p.box_n;
+  a.taps_w = p.taps_w; a.taps_h = p.taps_h; a.tap_sign = p.tap_sign;
+  a.org_h_off = p.a_h_off - (p.tap_sign > 0 ? 0 : p.taps_h - 1);
+  a.org_w_off = p.a_w_off - (p.tap_sign > 0 ? 0 : p.taps_w - 1);
+  a.k_chunks = p.a_c / kBlockK;
+  a.n_total = p.n_total;
+  a.xw = 8 + p.taps_w - 1;
+  const int halo_rows = (p.box_h + p.taps_h - 1) * p.box_n * a.xw;
+  a.a_tile_bytes = halo_rows * 128;
+  // the 16-group view may read past the loaded rows when box_h * box_n < 16: keep that inside the slot
+  const int view_rows = ((15 + (p.taps_h - 1) * p.box_n) * a.xw + (p.taps_w - 1) + 8);
+  a.a_slot_bytes = round_up((view_rows > halo_rows ? view_rows : halo_rows) * 128, 1024);
+  a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias; a.stat_partials = p.stat_partials;
+  a.relu = p.relu; a.out_fp32 = p.out_fp32;
+
+  const int total_kb = p.taps_h * p.taps_w * a.k_chunks;
+  const long long b_res_bytes = (long long)total_kb * kBStageBytes;
+  const bool resident = p.n_total == BN && b_res_bytes + 2 * a.a_slot_bytes + 4096 <= kMaxSmem && b_res_bytes < (1 << 20);
+  int budget = kMaxSmem - 4096;
+  if (resident) {
+    a.b_stages = 1;                       // unused ring, one dummy barrier pair
+    a.a_stages = std::min(4, (int)((budget - b_res_bytes) / a.a_slot_bytes));
+  } else {
+    a.a_stages = 2;
+    a.b_stages = std::min(8, (budget - a.a_stages * a.a_slot_bytes) / kBStageBytes);
+    if (a.b_stages >= 6 && budget - 3 * a.a_slot_bytes - 4 * kBStageBytes >= 0) {
+      a.a_stages = 3;
+      a.b_stages = std::min(8, (budget - a.a_stages * a.a_slot_bytes) / kBStageBytes);
+    }
+  }
+  if (a.a_stages < 2 || a.b_stages < 1) throw std::runtime_error("conv_gemm_halo: tile does not fit shared memory");
+  const size_t smem_bytes = 1024 + (size_t)a.a_stages * a.a_slot_bytes +
+                            (resident ? (size_t)b_res_bytes : (size_t)a.b_stages * kBStageBytes) +
+                            (2 * a.a_stages + 2 * a.b_stages + 5) * 8 + 16;
+  if (smem_bytes > (size_t)kMaxSmem) throw std::runtime_error("conv_gemm_halo: shared memory budget exceeded");
+
+  // A: (C, W, N, H) map, box (64, xw, box_n, box_h + taps_h - 1): halo brick rows ordered [h][n][w]
+  const uint64_t a_dims[4] = {(uint64_t)p.a_c, (uint64_t)p.a_w, (uint64_t)p.a_n, (uint64_t)p.a_h};
+  const uint64_t a_strides[3] = {(uint64_t)p.a_c * 2, (uint64_t)p.a_c * p.a_w * p.a_h * 2, (uint64_t)p.a_c * p.a_w * 2};
+  const uint32_t a_box[4] = {(uint32_t)kBlockK, (uint32_t)a.xw, (uint32_t)p.box_n, (uint32_t)(p.box_h + p.taps_h - 1)};
+  CUtensorMap tmap_a = make_tensor_map_bf16(p.a, 4, a_dims, a_strides, a_box);
+  CUtensorMap tmap_b;
+  const int num_taps = p.taps_h * p.taps_w;
+  if (!B_MN) {
+    const uint64_t b_dims[2] = {(uint64_t)num_taps * p.a_c, (uint64_t)p.n_total};
+    const uint64_t b_strides[1] = {(uint64_t)p.b_ld * 2};
+    const uint32_t b_box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
+  } else {
+    const uint64_t b_dims[2] = {(uint64_t)num_taps * p.n_total, (uint64_t)p.a_c};
+    const uint64_t b_strides[1] = {(uint64_t)p.b_ld * 2};
+    const uint32_t b_box[2] = {64u, (uint32_t)kBlockK};
+    tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
+  }
+  const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
+  const int tiles_n_cols = p.n_total / BN;
+  const int total_tiles = tiles_m * tiles_n_cols;
+  int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  grid -= grid % tiles_n_cols;
+  if (grid < tiles_n_cols) grid = tiles_n_cols;
+  auto run = [&](auto kernel) {
+    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
+  };
+  if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true>);
+  else run(conv_gemm_halo_kernel<BN, B_MN, false>);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+  return p.stat_partials != nullptr ? grid : tiles_m;
+}
+
+}  // namespace
+
+int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t stream) {
+  if (p.b_mn_major) {
+    switch (block_n) {
+      case 64: return launch_impl<64, true>(p, stream);
+      case 128: return launch_impl<128, true>(p, stream);
+      case 256: return launch_impl<256, true>(p, stream);
+    }
+  } else {
+    switch (block_n) {
+      case 64: return launch_impl<64, false>(p, stream);
+      case 128: return launch_impl<128, false>(p, stream);
+      case 256: return launch_impl<256, false>(p, stream);
+    }
+  }
+  throw std::runtime_error("conv_gemm_halo: block_n must be 64, 128 or 256");
+}
+
+}  // namespace ddpt

@@ -51,29 +51,33 @@ struct KernelArgs {
 };
 
 
-template <int BN, bool B_MN>
+// B_RES: the whole weight matrix (all taps x channel chunks of the single column block) is loaded into shared
+// memory once per CTA and stays resident; only activation bricks stream through the stage ring.  Halves (fwd) /
+// cuts by a third (dgrad) the L2->SM traffic of layers whose weights fit (Toy_Net conv.3: 144 KiB).
+template <int BN, bool B_MN, bool B_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
-  constexpr int kStages = stages_for<BN>();
+  constexpr int kStages = B_RES ? 4 : stages_for<BN>();
   constexpr int kBStageBytes = BN * kBlockK * 2;
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kAStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * kBStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;               // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int total_kb = args.num_taps * args.k_chunks;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kAStageBytes;         // B_RES: total_kb resident tiles, else kStages ring slots
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (B_RES ? total_kb : kStages) * kBStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;               // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                    // [2]
+  uint64_t* b_ready = tmem_empty + 2;                      // [1] resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -86,6 +90,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpilogueWarps);
     }
+    mbar_init(b_ready, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -97,7 +102,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx_bytes = args.a_rows_bytes + kBStageBytes;
+      const uint32_t tx_bytes = args.a_rows_bytes + (B_RES ? 0 : kBStageBytes);
+      if (B_RES) {                                         // one-time: every (tap, chunk) weight tile, column block 0
+        mbar_arrive_expect_tx(b_ready, static_cast<uint32_t>(total_kb) * kBStageBytes);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int tap = kb / args.k_chunks, chunk = kb - tap * args.k_chunks;
+          if (!B_MN) {
+            tma_load_2d(smem_b + kb * kBStageBytes, &tmap_b, b_ready, kb * kBlockK, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(smem_b + kb * kBStageBytes + j * (kBlockK * 128), &tmap_b, b_ready,
+                          tap * args.n_total + j * 64, chunk * kBlockK);
+          }
+        }
+      }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
@@ -116,7 +135,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(smem_a + s * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
                       w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
-          if (!B_MN) {
+          if (B_RES) {
+            // weights are resident
+          } else if (!B_MN) {
             tma_load_2d(smem_b + s * kBStageBytes, &tmap_b, &full_bar[s], kb * kBlockK, col0);
           } else {
 #pragma unroll
@@ -131,6 +152,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t it = 0, t = 0;
+      if (B_RES) mbar_wait(b_ready, 0, 5);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
@@ -142,7 +164,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           mbar_wait(&full_bar[s], phase, 2);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + s * kAStageBytes);
-          const uint32_t b_addr = smem_u32(smem_b + s * kBStageBytes);
+          const uint32_t b_addr = smem_u32(smem_b + (B_RES ? kb : s) * kBStageBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
@@ -269,11 +291,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   }
 }
 
-template <int BN, bool B_MN>
+template <int BN, bool B_MN, bool B_RES>
 int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
-  constexpr int kStages = stages_for<BN>();
+  constexpr int kStages = B_RES ? 4 : stages_for<BN>();
   constexpr int kBStageBytes = BN * kBlockK * 2;
-  const size_t smem_bytes = 1024 + kStages * (kAStageBytes + kBStageBytes) + (2 * kStages + 4) * 8 + 16;
+  const int total_kb_host = p.taps_h * p.taps_w * (p.a_c / kBlockK);
+  const size_t smem_bytes = 1024 + kStages * kAStageBytes + (size_t)(B_RES ? total_kb_host : kStages) * kBStageBytes +
+                            (2 * kStages + 5) * 8 + 16;
 
   KernelArgs a{};
   a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
@@ -312,10 +336,10 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
     tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
   }
 
-  auto kernel = conv_gemm_persistent_kernel<BN, B_MN>;
+  auto kernel = conv_gemm_persistent_kernel<BN, B_MN, B_RES>;
   static bool configured = false;
   if (!configured) {
-    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
@@ -332,17 +356,20 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
 }  // namespace
 
 int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream) {
+  // resident weights: one column block, and taps*C*BLOCK_N*2 bytes + a 4-deep activation ring fit in shared memory
+  const long long b_bytes = (long long)p.taps_h * p.taps_w * p.a_c * block_n * 2;
+  const bool resident = p.n_total == block_n && b_bytes + 4 * kAStageBytes + 2048 <= 227 * 1024 && b_bytes < (1 << 20);
   if (p.b_mn_major) {
     switch (block_n) {
-      case 64: return launch_persistent_impl<64, true>(p, stream);
-      case 128: return launch_persistent_impl<128, true>(p, stream);
-      case 256: return launch_persistent_impl<256, true>(p, stream);
+      case 64: return resident ? launch_persistent_impl<64, true, true>(p, stream) : launch_persistent_impl<64, true, false>(p, stream);
+      case 128: return resident ? launch_persistent_impl<128, true, true>(p, stream) : launch_persistent_impl<128, true, false>(p, stream);
+      case 256: return launch_persistent_impl<256, true, false>(p, stream);
     }
   } else {
     switch (block_n) {
-      case 64: return launch_persistent_impl<64, false>(p, stream);
-      case 128: return launch_persistent_impl<128, false>(p, stream);
-      case 256: return launch_persistent_impl<256, false>(p, stream);
+      case 64: return resident ? launch_persistent_impl<64, false, true>(p, stream) : launch_persistent_impl<64, false, false>(p, stream);
+      case 128: return resident ? launch_persistent_impl<128, false, true>(p, stream) : launch_persistent_impl<128, false, false>(p, stream);
+      case 256: return launch_persistent_impl<256, false, false>(p, stream);
     }
   }
   throw std::runtime_error("conv_gemm: block_n must be 64, 128 or 256");

@@ -50,6 +50,51 @@ def use_persistent(flag: Optional[bool] = None) -> bool:
     return os.environ.get("DDPT_GEMM_PERSISTENT", "1") != "0"
 
 
+@functools.lru_cache(maxsize=None)
+def pick_box_halo(out_n: int, out_h: int, out_w: int, kh: int = 3, kw: int = 3,
+                  max_slot_rows: int = 1 << 30) -> Tuple[Tuple[int, int, int], float]:
+    """Output brick for the halo-reuse kernel: 8 pixels wide, box_h * box_n <= 16 groups, halo tile (and the
+    16-group descriptor view) within ``max_slot_rows`` 128-byte rows; returns (box, fraction of useful MMA rows)."""
+    best, best_key = None, None
+    total = out_n * out_h * out_w
+    xw = 8 + kw - 1
+    for bh in range(1, min(out_h, 16) + 1):
+        for bn in range(1, min(out_n, 16 // bh) + 1):
+            halo_rows = (bh + kh - 1) * bn * xw
+            view_rows = (15 + (kh - 1) * bn) * xw + kw - 1 + 8
+            if max(halo_rows, view_rows) > max_slot_rows:
+                continue
+            tiles = -(-out_w // 8) * -(-out_h // bh) * -(-out_n // bn)
+            key = (round(total / (tiles * 128), 3), bh)
+            if best_key is None or key > best_key:
+                best, best_key = (bn, bh, 8), key
+    if best is None:
+        return None, 0.0
+    return best, best_key[0]
+
+
+def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: int, kw: int, c_k: int, n_total: int,
+               bn: int):
+    """(mode, box): 0 per-tile, 1 persistent, 2 persistent + halo reuse (see csrc/nn/conv_gemm_halo.cu)."""
+    if not use_persistent(persistent):
+        return 0, pick_box(*out_nhw)
+    env = os.environ.get("DDPT_GEMM_HALO", "1")
+    if halo is None and env == "force":
+        halo = True
+    want_halo = halo if halo is not None else env != "0"
+    if want_halo and kh * kw > 1:
+        b_bytes = kh * kw * c_k * bn * 2
+        resident = n_total == bn and b_bytes <= 150 * 1024
+        # resident weights leave (227 KiB - weights) / 2 per activation slot
+        max_rows = ((227 * 1024 - 4096 - b_bytes) // 2) // 128 if resident else 1 << 30
+        box, eff = pick_box_halo(*out_nhw, kh, kw, max_rows)
+        # worth it when the brick maps cleanly (>= 95 % useful rows), or when the layer is so L2-bound that
+        # resident weights + halo beat the row padding (small C_in / C_out: everything fits in shared memory)
+        if box is not None and (halo or eff >= 0.95 or (resident and eff >= 0.6)):
+            return 2, box
+    return 1, pick_box(*out_nhw)
+
+
 def _block_n(n_total: int, prefer: Optional[int]) -> int:
     if prefer is not None:
         return prefer
@@ -62,8 +107,10 @@ def _block_n(n_total: int, prefer: Optional[int]) -> int:
 def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Optional[int] = None,
                     device=None) -> int:
     """Row groups (x4 rows x 2 x C floats) a conv epilogue may write into ``stat_partials``."""
-    bn_, bh, bw = pick_box(out_n, out_h, out_w)
-    tiles_m = -(-out_w // bw) * -(-out_h // bh) * -(-out_n // bn_)
+    tiles_m = 0
+    for bn_, bh, bw in (pick_box(out_n, out_h, out_w), pick_box_halo(out_n, out_h, out_w, 3, 3, 300)[0],
+                        pick_box_halo(out_n, out_h, out_w)[0]):
+        tiles_m = max(tiles_m, -(-out_w // bw) * -(-out_h // bh) * -(-out_n // bn_))
     sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     return max(tiles_m, min(tiles_m * (c_out // _block_n(c_out, block_n)), sms))
 
@@ -71,7 +118,7 @@ def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Opt
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-             persistent: Optional[bool] = None):
+             persistent: Optional[bool] = None, halo: Optional[bool] = None):
     """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
     ext = require_native()
     n, h, w, c = x.shape
@@ -79,14 +126,15 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
     c_out = w_km.shape[0]
     if out is None:
         out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
-    box = pick_box(n, ho, wo)
+    bn = _block_n(c_out, block_n)
+    mode, box = (0, pick_box(n, ho, wo)) if split_k > 1 else _gemm_mode(persistent, halo, (n, ho, wo), kh, kw, c, c_out, bn)
     tiles = ext.conv_gemm(x, w_km, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], 1, [0, 0], False,
-                          bias, relu, stat_partials, split_k, _block_n(c_out, block_n), use_persistent(persistent))
+                          bias, relu, stat_partials, split_k, bn, mode)
     return out, tiles
 
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
-               block_n: Optional[int] = None, persistent: Optional[bool] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None):
     """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
@@ -94,9 +142,10 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
     c_in = w_km.shape[1] // (kh * kw)
     if out is None:
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
-    box = pick_box(n, h, w)
+    bn = _block_n(c_in, block_n)
+    mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn)
     ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
-                  None, False, None, 1, _block_n(c_in, block_n), use_persistent(persistent))
+                  None, False, None, 1, bn, mode)
     return out
 
 

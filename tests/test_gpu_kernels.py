@@ -14,10 +14,11 @@ def ext():
     return ops.require_native()
 
 
-@pytest.fixture(params=["persistent", "per_tile"], autouse=True)
+@pytest.fixture(params=["halo", "persistent", "per_tile"], autouse=True)
 def gemm_flavour(request, monkeypatch):
-    """Every GEMM/conv test runs against both forward/dgrad kernels (persistent and one-CTA-per-tile)."""
-    monkeypatch.setenv("DDPT_GEMM_PERSISTENT", "1" if request.param == "persistent" else "0")
+    """Every GEMM/conv test runs against all forward/dgrad kernels (halo reuse, persistent, one CTA per tile)."""
+    monkeypatch.setenv("DDPT_GEMM_PERSISTENT", "0" if request.param == "per_tile" else "1")
+    monkeypatch.setenv("DDPT_GEMM_HALO", "force" if request.param == "halo" else "0")
     return request.param
 
 
