@@ -174,7 +174,8 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
 
 // dy: [N,Ho,Wo,M] bf16, x: [N,H,W,C] bf16, dw: [M, taps_h, taps_w, C] fp32 (dense).
 void wgrad_gemm(at::Tensor dy, at::Tensor x, at::Tensor dw, std::vector<int64_t> taps_hw,
-                std::vector<int64_t> box_nhw, int64_t split_k, bool accumulate, int64_t block_n, bool multitap) {
+                std::vector<int64_t> box_nhw, int64_t split_k, bool accumulate, int64_t block_n, bool multitap,
+                c10::optional<at::Tensor> slab) {
   check_cuda(dy, "dy", at::kBFloat16); check_cuda(x, "x", at::kBFloat16); check_cuda(dw, "dw", at::kFloat);
   TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous() && x.dim() == 4 && x.is_contiguous() && dw.is_contiguous());
   TORCH_CHECK(dy.size(0) == x.size(0));
@@ -189,6 +190,11 @@ void wgrad_gemm(at::Tensor dy, at::Tensor x, at::Tensor dw, std::vector<int64_t>
   TORCH_CHECK(dw.numel() == (int64_t)p.m_total * p.taps_h * p.taps_w * p.c_total, "dw has the wrong size");
   p.dw = dw.data_ptr<float>();
   p.split_k = (int)split_k; p.accumulate = accumulate ? 1 : 0;
+  if (slab.has_value()) {
+    check_cuda(*slab, "slab", at::kFloat);
+    TORCH_CHECK(multitap && slab->is_contiguous() && slab->numel() >= std::max<int64_t>(split_k, 1) * dw.numel(), "slab too small");
+    p.slab = slab->data_ptr<float>();
+  }
   if (multitap) ddpt::launch_wgrad_gemm_multitap(p, (int)block_n, current_stream());
   else ddpt::launch_wgrad_gemm(p, (int)block_n, current_stream());
 }

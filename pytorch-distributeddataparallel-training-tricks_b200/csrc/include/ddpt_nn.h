@@ -61,6 +61,8 @@ struct WgradProblem {
   float* dw;                               // [M, taps_h, taps_w, C] fp32
   int split_k;                             // number of pixel-brick partitions (vector red.add when > 1)
   int accumulate;                          // 1: add into dw even when split_k == 1 (beta = 1)
+  float* slab;                             // multitap only: optional [split_k][M*taps*C] fp32 workspace; partials are
+                                           // stored there and folded by a reduction kernel instead of red.add
 };
 void launch_wgrad_gemm(const WgradProblem& p, int block_n, cudaStream_t stream);
 // Halo-reuse variant: one CTA accumulates a group of filter taps from a single dY + X(halo) brick load.

@@ -31,7 +31,8 @@ constexpr int kMaxSmem = 227 * 1024;
 constexpr int kMaxGroups = 9;
 
 struct TapGroup {
-  int r0, nr, s0, ns;          // filter rows [r0, r0+nr) x columns [s0, s0+ns)
+  int r0, nr, s0, ns;          // halo box: filter rows [r0, r0+nr) x columns [s0, s0+ns)
+  int mask;                    // which of the nr*ns taps inside the box this group accumulates (bit = dr*ns + ds)
   int map;                     // which X tensor map (box shape) this group uses
   int halo_rows;               // (bh + nr - 1) * bn * (bw + ns - 1)
 };
@@ -44,7 +45,10 @@ struct MtArgs {
   int stages, slot_a, slot_x;
   int num_groups;
   TapGroup groups[kMaxGroups];
-  float* dw;
+  float* dw;                   // final output (red.add) when slab == nullptr
+  float* slab;                 // optional [gridDim.z][M * taps * C] partial slabs written with plain stores
+  long long slab_elems;
+  int plain;                   // no slab, single split, beta = 0: plain stores straight into dw
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -71,7 +75,7 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
   const int gidx = blockIdx.y % args.num_groups;
   const int c0 = (blockIdx.y / args.num_groups) * BN;
   const TapGroup grp = args.groups[gidx];
-  const int group_taps = grp.nr * grp.ns;
+  const int box_taps = grp.nr * grp.ns;
 
   const int total_bricks = args.tiles_w * args.tiles_h * args.tiles_n;
   const int per_split = (total_bricks + gridDim.z - 1) / gridDim.z;
@@ -134,15 +138,19 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t x_addr = a_addr + kABlocks * args.slot_a;
-        for (int t = 0; t < group_taps; ++t) {
+        int acc_idx = 0;
+        for (int t = 0; t < box_taps; ++t) {
+          if (!((grp.mask >> t) & 1)) continue;
           const int dr = t / grp.ns, ds = t - dr * grp.ns;
+          const uint32_t tmem_d = tmem_base + acc_idx * BN;
+          ++acc_idx;
           for (int k = 0; k < k_steps; ++k) {
             const int g0 = 2 * k;                           // first of the two 8-pixel K groups of this step
             const int row = g0 / gpr, cg = g0 - row * gpr;  // (h, n) row of the brick, 8-pixel column group
             const uint32_t x_off = ((row + dr * args.box_n) * xw + cg * 8 + ds) * 128;
             const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
             const uint64_t bdesc = make_smem_desc(x_addr + x_off, args.slot_x, sbo_x);
-            mma_bf16_ss(tmem_base + t * BN, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
+            mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
           }
         }
         mma_commit(&empty_bar[s]);
@@ -155,17 +163,28 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     const int row = quad * 32 + lane;
     mbar_wait(accum_bar, 0, 33);
     tc_fence_after();
-    for (int t = 0; t < group_taps; ++t) {
+    float* dst_base = args.slab != nullptr ? args.slab + (long long)blockIdx.z * args.slab_elems : args.dw;
+    int acc_idx = 0;
+    for (int t = 0; t < box_taps; ++t) {
+      if (!((grp.mask >> t) & 1)) continue;
       const int dr = t / grp.ns, ds = t - dr * grp.ns;
       const int tap = (grp.r0 + dr) * args.taps_w + grp.s0 + ds;
-      float* out_row = args.dw + (static_cast<long long>(m0 + row) * args.num_taps + tap) * args.c_total + c0;
+      float* out_row = dst_base + (static_cast<long long>(m0 + row) * args.num_taps + tap) * args.c_total + c0;
+      const uint32_t tmem_t = tmem_base + acc_idx * BN;
+      ++acc_idx;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + t * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        tmem_ld_32x32(tmem_t + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
         tmem_ld_wait();
-        if (num_bricks > 0) {
-          float* o = out_row + c * 32;
+        float* o = out_row + c * 32;
+        if (args.slab != nullptr || args.plain) {
+          // every (split, tap, tile) slot of the slab is written exactly once: zeros when this split had no bricks
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(o + j) = num_bricks > 0 ? make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3])
+                                                              : make_uint4(0u, 0u, 0u, 0u);
+        } else if (num_bricks > 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             red_add_v4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -184,6 +203,27 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// out[i] (+)= sum over splits of slab[s][i]; 128-bit accesses, 4 independent loads in flight per thread.
+__global__ void __launch_bounds__(256)
+reduce_slabs_kernel(const float4* __restrict__ slab, float4* __restrict__ out, long long nvec, int splits,
+                    int accumulate) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
+    float4 acc = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      const float4 a = slab[(long long)s * nvec + i], b = slab[(long long)(s + 1) * nvec + i];
+      const float4 c = slab[(long long)(s + 2) * nvec + i], d = slab[(long long)(s + 3) * nvec + i];
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; s < splits; ++s) {
+      const float4 a = slab[(long long)s * nvec + i];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    out[i] = acc;
+  }
+}
+
 template <int BN>
 void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   MtArgs a{};
@@ -194,38 +234,57 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   a.tiles_n = (p.out_n + p.box_n - 1) / p.box_n;
   a.taps_w = p.taps_w; a.num_taps = p.taps_h * p.taps_w;
   a.c_total = p.c_total; a.dw = p.dw;
+  a.slab = p.slab;
+  a.plain = (p.slab == nullptr && p.split_k <= 1 && !p.accumulate) ? 1 : 0;
+  a.slab_elems = (long long)p.m_total * a.num_taps * p.c_total;
   const int gpr = p.box_w / 8;
   if (p.box_w % 8 != 0 || (gpr != 1 && gpr % 2 != 0) || a.brick_rows % kUmmaK != 0 || a.brick_rows > 128 ||
       p.m_total % kBlockM != 0 || p.c_total % BN != 0)
     throw std::runtime_error("wgrad_multitap: need box_w % 8 == 0 (1 or an even number of 8-pixel groups), "
                              "brick % 16 == 0, brick <= 128, M % 128 == 0, C % BLOCK_N == 0");
-  // tap groups: as many taps per CTA as fit 512 TMEM columns, cut along filter rows / columns
+  // tap groups: as many taps per CTA as fit 512 TMEM columns.  When whole filter rows fit, taps are dealt out
+  // evenly in row-major order (e.g. 9 taps, 8 fit -> 5 + 4) and a group's halo box spans the rows it touches;
+  // otherwise a row is cut into column ranges.
   const int max_taps = 512 / BN;
-  int rows_per_group = 1, cols_per_group = p.taps_w;
-  if (max_taps >= p.taps_w) rows_per_group = std::min(p.taps_h, max_taps / p.taps_w);
-  else cols_per_group = max_taps;
+  const int total_taps = p.taps_h * p.taps_w;
   int max_group_taps = 0, max_halo = 0;
   uint32_t shapes[2][2] = {{0, 0}, {0, 0}};
   int num_shapes = 0;
-  for (int r0 = 0; r0 < p.taps_h; r0 += rows_per_group)
-    for (int s0 = 0; s0 < p.taps_w; s0 += cols_per_group) {
-      TapGroup g{};
-      g.r0 = r0; g.nr = std::min(rows_per_group, p.taps_h - r0);
-      g.s0 = s0; g.ns = std::min(cols_per_group, p.taps_w - s0);
-      g.halo_rows = (p.box_h + g.nr - 1) * p.box_n * (p.box_w + g.ns - 1);
-      g.map = -1;
-      for (int k = 0; k < num_shapes; ++k)
-        if (shapes[k][0] == (uint32_t)g.nr && shapes[k][1] == (uint32_t)g.ns) g.map = k;
-      if (g.map < 0) {
-        if (num_shapes == 2) throw std::runtime_error("wgrad_multitap: more than two halo shapes");
-        shapes[num_shapes][0] = g.nr; shapes[num_shapes][1] = g.ns;
-        g.map = num_shapes++;
-      }
-      if (a.num_groups == kMaxGroups) throw std::runtime_error("wgrad_multitap: too many tap groups");
-      a.groups[a.num_groups++] = g;
-      max_group_taps = std::max(max_group_taps, g.nr * g.ns);
-      max_halo = std::max(max_halo, g.halo_rows);
+  auto add_group = [&](TapGroup g) {
+    g.halo_rows = (p.box_h + g.nr - 1) * p.box_n * (p.box_w + g.ns - 1);
+    g.map = -1;
+    for (int k = 0; k < num_shapes; ++k)
+      if (shapes[k][0] == (uint32_t)g.nr && shapes[k][1] == (uint32_t)g.ns) g.map = k;
+    if (g.map < 0) {
+      if (num_shapes == 2) throw std::runtime_error("wgrad_multitap: more than two halo shapes");
+      shapes[num_shapes][0] = g.nr; shapes[num_shapes][1] = g.ns;
+      g.map = num_shapes++;
     }
+    if (a.num_groups == kMaxGroups) throw std::runtime_error("wgrad_multitap: too many tap groups");
+    a.groups[a.num_groups++] = g;
+    max_group_taps = std::max(max_group_taps, __builtin_popcount(g.mask));
+    max_halo = std::max(max_halo, g.halo_rows);
+  };
+  if (max_taps >= p.taps_w) {
+    const int ngroups = (total_taps + max_taps - 1) / max_taps;
+    for (int k = 0; k < ngroups; ++k) {
+      const int t0 = (int)((long long)total_taps * k / ngroups), t1 = (int)((long long)total_taps * (k + 1) / ngroups);
+      TapGroup g{};
+      g.r0 = t0 / p.taps_w;
+      g.nr = (t1 - 1) / p.taps_w - g.r0 + 1;
+      g.s0 = 0; g.ns = p.taps_w;
+      for (int t = t0; t < t1; ++t) g.mask |= 1 << (t - g.r0 * p.taps_w);
+      add_group(g);
+    }
+  } else {
+    for (int r0 = 0; r0 < p.taps_h; ++r0)
+      for (int s0 = 0; s0 < p.taps_w; s0 += max_taps) {
+        TapGroup g{};
+        g.r0 = r0; g.nr = 1; g.s0 = s0; g.ns = std::min(max_taps, p.taps_w - s0);
+        g.mask = (1 << g.ns) - 1;
+        add_group(g);
+      }
+  }
   if (max_halo > 256) throw std::runtime_error("wgrad_multitap: halo brick exceeds a 256-row TMA box");
   a.slot_a = round_up(a.brick_rows * 128, 1024);
   a.slot_x = round_up(max_halo * 128, 1024);
@@ -259,6 +318,14 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   else if (cols <= 256) run(wgrad_multitap_kernel<BN, 256>);
   else run(wgrad_multitap_kernel<BN, 512>);
   DDPT_CUDA_CHECK(cudaGetLastError());
+  if (p.slab != nullptr) {
+    const long long nvec = a.slab_elems / 4;
+    long long want = (nvec + 255) / 256;
+    const int blocks = (int)std::min<long long>(want, (long long)sm_count() * 8);
+    reduce_slabs_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(p.slab),
+                                                    reinterpret_cast<float4*>(p.dw), nvec, (int)grid.z, p.accumulate);
+    DDPT_CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 }  // namespace

@@ -173,6 +173,18 @@ def pick_box_multitap(out_n: int, out_h: int, out_w: int, max_rows: int = 128) -
     return best
 
 
+_SLABS = {}
+
+
+def _slab(device, numel: int) -> torch.Tensor:
+    """Cached split-K workspace (fp32); grown on demand, never inside a CUDA-graph capture."""
+    key = str(device)
+    buf = _SLABS.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = _SLABS[key] = torch.empty(numel, dtype=torch.float32, device=device)
+    return buf
+
+
 def use_multitap(flag: Optional[bool] = None) -> bool:
     """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu); DDPT_WGRAD_MULTITAP=0 disables."""
     if flag is not None:
@@ -189,23 +201,28 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
     c_in = x.shape[3]
     bn = _block_n(c_in, block_n)
     mt = use_multitap(multitap)
+    bricks_of = lambda b: -(-wo // b[2]) * -(-ho // b[1]) * -(-n // b[0])
+    sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
+    slab = None
     if mt:
         box = pick_box_multitap(n, ho, wo, 128 if bn <= 128 else 64)
         max_taps = 512 // bn
-        groups = (-(-kh // max(1, min(kh, max_taps // kw)))) if max_taps >= kw else kh * -(-kw // max_taps)
+        groups = -(-(kh * kw) // max_taps) if max_taps >= kw else kh * -(-kw // max_taps)
         ctas = (c_out // 128) * groups * (c_in // bn)
+        if split_k is None:      # one resident CTA per SM (the stage ring fills shared memory): a single wave
+            split_k = max(1, min(bricks_of(box), sms // ctas))
+        if split_k > 1:
+            slab = _slab(dy.device, split_k * c_out * kh * kw * c_in)
     else:
         box = pick_box(n, ho, wo, 16)
         ctas = (c_out // 128) * kh * kw * (c_in // bn)
-    if split_k is None:
-        bricks = -(-wo // box[2]) * -(-ho // box[1]) * -(-n // box[0])
-        sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
-        split_k = max(1, min(bricks, -(-2 * sms // ctas)))
+        if split_k is None:
+            split_k = max(1, min(bricks_of(box), -(-2 * sms // ctas)))
     if out is None:
         out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
-    elif not accumulate and (split_k > 1 or mt):
+    elif not accumulate and slab is None and split_k > 1:
         out.zero_()
-    ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn, mt)
+    ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn, mt, slab)
     return out
 
 

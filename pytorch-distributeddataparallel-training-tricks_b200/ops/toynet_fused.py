@@ -194,7 +194,7 @@ class FusedToyNet:
         self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=17)
         ready(19); ready(18); ready(17)
         dy4 = ws.dy[4]
-        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], accumulate=True)
+        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16])
         ready(16)
         g = gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
         g = ws.da[3]
@@ -203,7 +203,7 @@ class FusedToyNet:
             h_out = h_in - 2
             self._bn_backward(k, ws, g, grads, pool, k == 3, batch * float(h_out * h_out), dbias_idx=pidx + 1)
             ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
-            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx], accumulate=True)
+            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx])
             ready(pidx)
             g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
         self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
