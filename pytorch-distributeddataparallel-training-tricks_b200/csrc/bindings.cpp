@@ -227,8 +227,32 @@ static at::Tensor umma_probe(at::Tensor a, at::Tensor b, std::vector<int64_t> cf
   return out;
 }
 
+namespace ddpt {
+struct MxProbeArgs {
+  const uint32_t* sfa_words; const uint32_t* sfb_words;
+  int sfa_col, sfb_col, sf_id_mode, ksteps;
+  float* out;
+};
+void launch_umma_mx_probe(const void* a_fp8, const void* b_fp8, const MxProbeArgs& p, cudaStream_t stream);
+}  // namespace ddpt
+
+static at::Tensor umma_mx_probe(at::Tensor a, at::Tensor b, at::Tensor sfa, at::Tensor sfb, int64_t sfa_col,
+                                int64_t sfb_col, int64_t sf_id_mode, int64_t ksteps) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kByte && a.numel() == 128 * 128 && a.is_contiguous());
+  TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kByte && b.numel() == 64 * 128 && b.is_contiguous());
+  TORCH_CHECK(sfa.scalar_type() == at::kInt && sfa.numel() == 512 && sfb.scalar_type() == at::kInt && sfb.numel() == 512);
+  c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor out = at::zeros({128, 64}, a.options().dtype(at::kFloat));
+  ddpt::MxProbeArgs p{reinterpret_cast<const uint32_t*>(sfa.data_ptr<int>()),
+                      reinterpret_cast<const uint32_t*>(sfb.data_ptr<int>()), (int)sfa_col, (int)sfb_col,
+                      (int)sf_id_mode, (int)ksteps, out.data_ptr<float>()};
+  ddpt::launch_umma_mx_probe(a.data_ptr(), b.data_ptr(), p, at::cuda::getCurrentCUDAStream().stream());
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("umma_probe", &umma_probe);
+  m.def("umma_mx_probe", &umma_mx_probe);
   m.doc() = "ddpt_b200 sm_100a kernels";
   m.def("multi_tensor_scale", &multi_tensor_scale);
   m.def("multi_tensor_axpby", &multi_tensor_axpby);

@@ -2,11 +2,14 @@
 //
 // conv_gemm_persistent.cu streams one activation brick per (filter tap, 64-channel chunk): every input pixel
 // crosses L2->SM nine times and the layer is L2-bandwidth bound when C_in / C_out are small (Toy_Net conv.3).
-// Here the brick is loaded ONCE per channel chunk together with its halo,
-//     [(bh + kh - 1) rows][bn images][(8 + kw - 1) pixels][64 channels]     (TMA box over a (C, W, N, H) map)
-// and each of the kh*kw taps is a *descriptor view* into that tile: start address shifted by whole 128-byte
-// pixel rows, 8-pixel groups (8 + kw - 1) * 128 bytes apart.  tcgen05.mma swizzles on absolute shared-memory
-// addresses (profiles/umma_descriptor_probe.txt), so the views need no copy.  Weights either stay resident in
+// Here a brick is loaded once per (channel chunk, filter COLUMN) together with its row halo,
+//     [(bh + kh - 1) rows][bn images][8 pixels][64 channels]                (TMA box over a (C, W, N, H) map)
+// and the kh taps of that filter column are *descriptor views* into the tile: the start address moves by whole
+// 1024-byte swizzle atoms (one 8-pixel group per (row, image)), so every view stays atom-aligned.  (Views shifted
+// by single pixels also compute correctly -- tcgen05.mma swizzles on absolute shared-memory addresses,
+// profiles/umma_descriptor_probe.txt -- but an 8-row group that straddles two atoms costs two shared-memory
+// fetches and the kernel becomes operand-fetch bound; measured in profiles/.)  Activation traffic drops from
+// kh*kw to kw*(bh+kh-1)/bh bricks per chunk (3.75 instead of 9 for 3x3, bh = 8).  Weights either stay resident in
 // shared memory for the whole kernel (when all taps x chunks x BLOCK_N fit: conv.3) or stream through their
 // own ring.  Output tiles are 16 groups of 8 consecutive pixels ordered (h, n, w); everything else -- warp
 // roles, double-buffered TMEM accumulator, bias / ReLU / BatchNorm-statistics epilogue -- matches the
@@ -37,7 +40,6 @@ struct HaloArgs {
   int taps_w, taps_h, tap_sign;
   int org_h_off, org_w_off;         // halo tile origin relative to the tile's (h0, w0)
   int k_chunks, n_total;
-  int xw;                           // halo row width in pixels = 8 + taps_w - 1
   int a_slot_bytes, a_tile_bytes;
   int a_stages, b_stages;
   long long ld_out;
@@ -115,18 +117,22 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int th = (tile_m / args.tiles_w) % args.tiles_h;
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * 8, h0 = th * args.box_h, n0 = tn * args.box_n;
-        for (int chunk = 0; chunk < args.k_chunks; ++chunk, ++ia) {
-          const int sa = ia % args.a_stages;
-          mbar_wait(&a_empty[sa], ((ia / args.a_stages) & 1) ^ 1, 41);
-          mbar_arrive_expect_tx(&a_full[sa], args.a_tile_bytes);
-          tma_load_4d(smem_a + sa * args.a_slot_bytes, &tmap_a, &a_full[sa], chunk * kBlockK, w0 + args.org_w_off, n0,
-                      h0 + args.org_h_off);
-          if (!B_RES) {
-            for (int tap = 0; tap < num_taps; ++tap, ++ib) {
-              const int sb = ib % args.b_stages;
-              mbar_wait(&b_empty[sb], ((ib / args.b_stages) & 1) ^ 1, 42);
-              mbar_arrive_expect_tx(&b_full[sb], kBStageBytes);
-              load_b(smem_b + sb * kBStageBytes, &b_full[sb], tap, chunk, tile_n * BN);
+        for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
+          for (int cs = 0; cs < args.taps_w; ++cs, ++ia) {       // one activation brick per filter column
+            const int sa = ia % args.a_stages;
+            mbar_wait(&a_empty[sa], ((ia / args.a_stages) & 1) ^ 1, 41);
+            mbar_arrive_expect_tx(&a_full[sa], args.a_tile_bytes);
+            tma_load_4d(smem_a + sa * args.a_slot_bytes, &tmap_a, &a_full[sa], chunk * kBlockK,
+                        w0 + args.org_w_off + cs, n0, h0 + args.org_h_off);
+            if (!B_RES) {
+              for (int dr = 0; dr < args.taps_h; ++dr, ++ib) {
+                const int r = args.tap_sign > 0 ? dr : args.taps_h - 1 - dr;
+                const int sx = args.tap_sign > 0 ? cs : args.taps_w - 1 - cs;
+                const int sb = ib % args.b_stages;
+                mbar_wait(&b_empty[sb], ((ib / args.b_stages) & 1) ^ 1, 42);
+                mbar_arrive_expect_tx(&b_full[sb], kBStageBytes);
+                load_b(smem_b + sb * kBStageBytes, &b_full[sb], r * args.taps_w + sx, chunk, tile_n * BN);
+              }
             }
           }
         }
@@ -136,44 +142,45 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ===== MMA issuer: every tap is a shifted view of the halo brick =====
     if (lane == 0) {
       uint32_t ia = 0, ib = 0, t = 0;
-      const uint32_t sbo_a = args.xw * 128;
       if (B_RES) mbar_wait(b_ready, 0, 45);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 44);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int chunk = 0; chunk < args.k_chunks; ++chunk, ++ia) {
-          const int sa = ia % args.a_stages;
-          mbar_wait(&a_full[sa], (ia / args.a_stages) & 1, 43);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + sa * args.a_slot_bytes);
-          for (int tap = 0; tap < num_taps; ++tap) {
-            const int r = tap / args.taps_w, s = tap - r * args.taps_w;
-            const int dr = args.tap_sign > 0 ? r : args.taps_h - 1 - r;
-            const int ds = args.tap_sign > 0 ? s : args.taps_w - 1 - s;
-            uint32_t b_addr;
-            int sb = 0;
-            if (B_RES) {
-              b_addr = smem_u32(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes);
-            } else {
-              sb = ib % args.b_stages;
-              mbar_wait(&b_full[sb], (ib / args.b_stages) & 1, 46);
-              tc_fence_after();
-              b_addr = smem_u32(smem_b + sb * kBStageBytes);
-              ++ib;
-            }
-            const uint32_t a_view = a_addr + ((dr * args.box_n) * args.xw + ds) * 128;
+        for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
+          for (int cs = 0; cs < args.taps_w; ++cs, ++ia) {
+            const int sa = ia % args.a_stages;
+            mbar_wait(&a_full[sa], (ia / args.a_stages) & 1, 43);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + sa * args.a_slot_bytes);
+            for (int dr = 0; dr < args.taps_h; ++dr) {
+              const int r = args.tap_sign > 0 ? dr : args.taps_h - 1 - dr;
+              const int sx = args.tap_sign > 0 ? cs : args.taps_w - 1 - cs;
+              const int tap = r * args.taps_w + sx;
+              uint32_t b_addr;
+              int sb = 0;
+              if (B_RES) {
+                b_addr = smem_u32(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes);
+              } else {
+                sb = ib % args.b_stages;
+                mbar_wait(&b_full[sb], (ib / args.b_stages) & 1, 46);
+                tc_fence_after();
+                b_addr = smem_u32(smem_b + sb * kBStageBytes);
+                ++ib;
+              }
+              const uint32_t a_view = a_addr + (dr * args.box_n) * 1024;     // whole swizzle atoms: aligned view
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t adesc = make_smem_desc(a_view + k * (kUmmaK * 2), 0, sbo_a);
-              const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
-                                          : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
-              mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (chunk | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t adesc = make_smem_desc(a_view + k * (kUmmaK * 2), 0, 1024);
+                const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
+                                            : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
+                mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (chunk | cs | dr | k) != 0 ? 1u : 0u);
+              }
+              if (!B_RES) mma_commit(&b_empty[sb]);
             }
-            if (!B_RES) mma_commit(&b_empty[sb]);
+            mma_commit(&a_empty[sa]);
           }
-          mma_commit(&a_empty[sa]);
         }
         mma_commit(&tmem_full[acc]);
       }
@@ -305,29 +312,25 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.org_w_off = p.a_w_off - (p.tap_sign > 0 ? 0 : p.taps_w - 1);
   a.k_chunks = p.a_c / kBlockK;
   a.n_total = p.n_total;
-  a.xw = 8 + p.taps_w - 1;
-  const int halo_rows = (p.box_h + p.taps_h - 1) * p.box_n * a.xw;
+  const int halo_rows = (p.box_h + p.taps_h - 1) * p.box_n * 8;
   a.a_tile_bytes = halo_rows * 128;
   // the 16-group view may read past the loaded rows when box_h * box_n < 16: keep that inside the slot
-  const int view_rows = ((15 + (p.taps_h - 1) * p.box_n) * a.xw + (p.taps_w - 1) + 8);
+  const int view_rows = (16 + (p.taps_h - 1) * p.box_n) * 8;
   a.a_slot_bytes = round_up((view_rows > halo_rows ? view_rows : halo_rows) * 128, 1024);
   a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias; a.stat_partials = p.stat_partials;
   a.relu = p.relu; a.out_fp32 = p.out_fp32;
 
   const int total_kb = p.taps_h * p.taps_w * a.k_chunks;
   const long long b_res_bytes = (long long)total_kb * kBStageBytes;
-  const bool resident = p.n_total == BN && b_res_bytes + 2 * a.a_slot_bytes + 4096 <= kMaxSmem && b_res_bytes < (1 << 20);
-  int budget = kMaxSmem - 4096;
+  int budget = kMaxSmem - 2048;
+  const bool resident = p.n_total == BN && b_res_bytes + 3 * a.a_slot_bytes <= budget && b_res_bytes < (1 << 20);
   if (resident) {
     a.b_stages = 1;                       // unused ring, one dummy barrier pair
-    a.a_stages = std::min(4, (int)((budget - b_res_bytes) / a.a_slot_bytes));
+    a.a_stages = std::min(6, (int)((budget - b_res_bytes) / a.a_slot_bytes));
   } else {
-    a.a_stages = 2;
+    // split the budget roughly 1:1 between activation bricks and weight tiles, at least 3 bricks in flight
+    a.a_stages = std::max(3, std::min(5, (budget / 2) / a.a_slot_bytes));
     a.b_stages = std::min(8, (budget - a.a_stages * a.a_slot_bytes) / kBStageBytes);
-    if (a.b_stages >= 6 && budget - 3 * a.a_slot_bytes - 4 * kBStageBytes >= 0) {
-      a.a_stages = 3;
-      a.b_stages = std::min(8, (budget - a.a_stages * a.a_slot_bytes) / kBStageBytes);
-    }
   }
   if (a.a_stages < 2 || a.b_stages < 1) throw std::runtime_error("conv_gemm_halo: tile does not fit shared memory");
   const size_t smem_bytes = 1024 + (size_t)a.a_stages * a.a_slot_bytes +
@@ -335,10 +338,10 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
                             (2 * a.a_stages + 2 * a.b_stages + 5) * 8 + 16;
   if (smem_bytes > (size_t)kMaxSmem) throw std::runtime_error("conv_gemm_halo: shared memory budget exceeded");
 
-  // A: (C, W, N, H) map, box (64, xw, box_n, box_h + taps_h - 1): halo brick rows ordered [h][n][w]
+  // A: (C, W, N, H) map, box (64, 8, box_n, box_h + taps_h - 1): row-halo brick, rows ordered [h][n][w]
   const uint64_t a_dims[4] = {(uint64_t)p.a_c, (uint64_t)p.a_w, (uint64_t)p.a_n, (uint64_t)p.a_h};
   const uint64_t a_strides[3] = {(uint64_t)p.a_c * 2, (uint64_t)p.a_c * p.a_w * p.a_h * 2, (uint64_t)p.a_c * p.a_w * 2};
-  const uint32_t a_box[4] = {(uint32_t)kBlockK, (uint32_t)a.xw, (uint32_t)p.box_n, (uint32_t)(p.box_h + p.taps_h - 1)};
+  const uint32_t a_box[4] = {(uint32_t)kBlockK, 8u, (uint32_t)p.box_n, (uint32_t)(p.box_h + p.taps_h - 1)};
   CUtensorMap tmap_a = make_tensor_map_bf16(p.a, 4, a_dims, a_strides, a_box);
   CUtensorMap tmap_b;
   const int num_taps = p.taps_h * p.taps_w;

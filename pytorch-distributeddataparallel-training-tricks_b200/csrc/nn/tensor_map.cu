@@ -23,8 +23,8 @@ PFN_cuTensorMapEncodeTiled_v12000 resolve_encode() {
 
 }  // namespace
 
-CUtensorMap make_tensor_map_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box) {
+static CUtensorMap make_tensor_map_typed(CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                                         const uint64_t* strides_bytes, const uint32_t* box) {
   CUtensorMap map;
   cuuint64_t gdim[5];
   cuuint64_t gstride[4];
@@ -36,7 +36,7 @@ CUtensorMap make_tensor_map_bf16(const void* base, int rank, const uint64_t* dim
     estride[i] = 1;
     if (i > 0) gstride[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = resolve_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = resolve_encode()(&map, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                                 gdim, gstride, bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -47,6 +47,16 @@ CUtensorMap make_tensor_map_bf16(const void* base, int rank, const uint64_t* dim
     throw std::runtime_error(msg);
   }
   return map;
+}
+
+CUtensorMap make_tensor_map_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box) {
+  return make_tensor_map_typed(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
+CUtensorMap make_tensor_map_u8(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                               const uint32_t* box) {
+  return make_tensor_map_typed(CU_TENSOR_MAP_DATA_TYPE_UINT8, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace ddpt

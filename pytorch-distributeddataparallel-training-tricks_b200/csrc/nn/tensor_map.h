@@ -11,5 +11,8 @@ namespace ddpt {
 // out-of-bounds elements read as zero.
 CUtensorMap make_tensor_map_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                                  const uint32_t* box);
+// Same for 1-byte elements (fp8 operands of the block-scaled path).
+CUtensorMap make_tensor_map_u8(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                               const uint32_t* box);
 
 }  // namespace ddpt

@@ -193,10 +193,25 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
   const int c = blockIdx.x * 32 + lane;
   double sum = 0.0, sq = 0.0;
   if (c < channels) {
-    for (int p = grp; p < num_partials; p += kFinGroups) {
-      sum += (double)partials[((size_t)p * 2) * channels + c];
-      sq += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    // 4 row groups per trip with independent accumulators: the loads of a trip are all in flight together
+    double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+    int p = grp;
+    for (; p + 3 * kFinGroups < num_partials; p += 4 * kFinGroups) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = partials[((size_t)(p + u * kFinGroups) * 2) * channels + c];
+        b[u] = partials[((size_t)(p + u * kFinGroups) * 2 + 1) * channels + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s4[u] += (double)a[u]; q4[u] += (double)b[u]; }
     }
+    for (; p < num_partials; p += kFinGroups) {
+      s4[0] += (double)partials[((size_t)p * 2) * channels + c];
+      q4[0] += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    }
+    sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   }
   s_sum[grp][lane] = sum;
   s_sq[grp][lane] = sq;
@@ -427,10 +442,24 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
   const int c = blockIdx.x * 32 + lane;
   double a = 0.0, b = 0.0;
   if (c < channels) {
-    for (int p = grp; p < num_partials; p += kFinGroups) {
-      a += (double)partials[((size_t)p * 2) * channels + c];
-      b += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+    int p = grp;
+    for (; p + 3 * kFinGroups < num_partials; p += 4 * kFinGroups) {
+      float x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        x[u] = partials[((size_t)(p + u * kFinGroups) * 2) * channels + c];
+        y[u] = partials[((size_t)(p + u * kFinGroups) * 2 + 1) * channels + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a4[u] += (double)x[u]; b4[u] += (double)y[u]; }
     }
+    for (; p < num_partials; p += kFinGroups) {
+      a4[0] += (double)partials[((size_t)p * 2) * channels + c];
+      b4[0] += (double)partials[((size_t)p * 2 + 1) * channels + c];
+    }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
   }
   s_a[grp][lane] = a;
   s_b[grp][lane] = b;

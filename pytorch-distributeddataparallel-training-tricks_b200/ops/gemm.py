@@ -57,11 +57,10 @@ def pick_box_halo(out_n: int, out_h: int, out_w: int, kh: int = 3, kw: int = 3,
     16-group descriptor view) within ``max_slot_rows`` 128-byte rows; returns (box, fraction of useful MMA rows)."""
     best, best_key = None, None
     total = out_n * out_h * out_w
-    xw = 8 + kw - 1
     for bh in range(1, min(out_h, 16) + 1):
         for bn in range(1, min(out_n, 16 // bh) + 1):
-            halo_rows = (bh + kh - 1) * bn * xw
-            view_rows = (15 + (kh - 1) * bn) * xw + kw - 1 + 8
+            halo_rows = (bh + kh - 1) * bn * 8             # one brick per filter column: row halo only
+            view_rows = (16 + (kh - 1) * bn) * 8
             if max(halo_rows, view_rows) > max_slot_rows:
                 continue
             tiles = -(-out_w // 8) * -(-out_h // bh) * -(-out_n // bn)
@@ -85,8 +84,8 @@ def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: in
     if want_halo and kh * kw > 1:
         b_bytes = kh * kw * c_k * bn * 2
         resident = n_total == bn and b_bytes <= 150 * 1024
-        # resident weights leave (227 KiB - weights) / 2 per activation slot
-        max_rows = ((227 * 1024 - 4096 - b_bytes) // 2) // 128 if resident else 1 << 30
+        # resident weights leave (227 KiB - weights) / 3 per activation slot (three bricks in flight)
+        max_rows = ((227 * 1024 - 2048 - b_bytes) // 3) // 128 if resident else 1 << 30
         box, eff = pick_box_halo(*out_nhw, kh, kw, max_rows)
         # worth it when the brick maps cleanly (>= 95 % useful rows), or when the layer is so L2-bound that
         # resident weights + halo beat the row padding (small C_in / C_out: everything fits in shared memory)
