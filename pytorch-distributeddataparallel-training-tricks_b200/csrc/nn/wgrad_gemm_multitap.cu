@@ -265,26 +265,19 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
     max_group_taps = std::max(max_group_taps, __builtin_popcount(g.mask));
     max_halo = std::max(max_halo, g.halo_rows);
   };
-  if (max_taps >= p.taps_w) {
-    const int ngroups = (total_taps + max_taps - 1) / max_taps;
-    for (int k = 0; k < ngroups; ++k) {
-      const int t0 = (int)((long long)total_taps * k / ngroups), t1 = (int)((long long)total_taps * (k + 1) / ngroups);
+  // One group per filter COLUMN s: its taps (r = 0..kh-1, split when they do not fit TMEM) share an X brick with a
+  // row halo only, so every tap view starts on a 1024-byte swizzle-atom boundary (ds = 0).  Pixel-shifted views
+  // are legal but an 8-row group straddling two atoms doubles the operand fetches (see conv_gemm_halo.cu).
+  (void)total_taps;
+  const int rows_per_group = std::max(1, std::min(p.taps_h, max_taps));
+  for (int s0 = 0; s0 < p.taps_w; ++s0)
+    for (int r0 = 0; r0 < p.taps_h; r0 += rows_per_group) {
       TapGroup g{};
-      g.r0 = t0 / p.taps_w;
-      g.nr = (t1 - 1) / p.taps_w - g.r0 + 1;
-      g.s0 = 0; g.ns = p.taps_w;
-      for (int t = t0; t < t1; ++t) g.mask |= 1 << (t - g.r0 * p.taps_w);
+      g.r0 = r0; g.nr = std::min(rows_per_group, p.taps_h - r0);
+      g.s0 = s0; g.ns = 1;
+      g.mask = (1 << g.nr) - 1;
       add_group(g);
     }
-  } else {
-    for (int r0 = 0; r0 < p.taps_h; ++r0)
-      for (int s0 = 0; s0 < p.taps_w; s0 += max_taps) {
-        TapGroup g{};
-        g.r0 = r0; g.nr = 1; g.s0 = s0; g.ns = std::min(max_taps, p.taps_w - s0);
-        g.mask = (1 << g.ns) - 1;
-        add_group(g);
-      }
-  }
   if (max_halo > 256) throw std::runtime_error("wgrad_multitap: halo brick exceeds a 256-row TMA box");
   a.slot_a = round_up(a.brick_rows * 128, 1024);
   a.slot_x = round_up(max_halo * 128, 1024);

@@ -87,9 +87,10 @@ def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: in
         # resident weights leave (227 KiB - weights) / 3 per activation slot (three bricks in flight)
         max_rows = ((227 * 1024 - 2048 - b_bytes) // 3) // 128 if resident else 1 << 30
         box, eff = pick_box_halo(*out_nhw, kh, kw, max_rows)
-        # worth it when the brick maps cleanly (>= 95 % useful rows), or when the layer is so L2-bound that
-        # resident weights + halo beat the row padding (small C_in / C_out: everything fits in shared memory)
-        if box is not None and (halo or eff >= 0.95 or (resident and eff >= 0.6)):
+        # measured (profiles/kernel_probe_*.json): the halo variant wins only when the weights are resident AND
+        # the 8-pixel bricks tile the output exactly (Toy_Net conv.3 forward: 866 vs 758 TFLOP/s); row padding or
+        # streamed weights make it lose to the plain persistent kernel, so those cases stay on mode 1
+        if box is not None and (halo or (resident and eff >= 0.95)):
             return 2, box
     return 1, pick_box(*out_nhw)
 
@@ -206,7 +207,7 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
     if mt:
         box = pick_box_multitap(n, ho, wo, 128 if bn <= 128 else 64)
         max_taps = 512 // bn
-        groups = -(-(kh * kw) // max_taps) if max_taps >= kw else kh * -(-kw // max_taps)
+        groups = kw * -(-kh // max(1, min(kh, max_taps)))      # one group per filter column (x row splits)
         ctas = (c_out // 128) * groups * (c_in // bn)
         if split_k is None:      # one resident CTA per SM (the stage ring fills shared memory): a single wave
             split_k = max(1, min(bricks_of(box), sms // ctas))
