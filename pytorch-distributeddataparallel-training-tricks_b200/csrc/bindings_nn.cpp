@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 
 #include "include/ddpt_toynet.h"
+#include "include/ddpt_fp8.h"
 
 namespace {
 
@@ -151,9 +152,61 @@ void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> ta
   ddpt::launch_head(h, cur());
 }
 
+// x: [rows, cols] bf16/fp32 contiguous (cols % 32 == 0) -> (uint8 e4m3 [rows, cols], uint8 UE8M0 [rows, cols/32])
+std::pair<at::Tensor, at::Tensor> quantize_mxfp8(at::Tensor x, c10::optional<at::Tensor> data_out,
+                                                 c10::optional<at::Tensor> scale_out) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kFloat));
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  TORCH_CHECK(cols % 32 == 0, "quantize_mxfp8: the last dimension must be a multiple of 32");
+  c10::cuda::CUDAGuard g(x.device());
+  auto shape = x.sizes().vec();
+  at::Tensor data = data_out.has_value() ? *data_out : at::empty(shape, x.options().dtype(at::kByte));
+  shape.back() = cols / 32;
+  at::Tensor scale = scale_out.has_value() ? *scale_out : at::empty(shape, x.options().dtype(at::kByte));
+  TORCH_CHECK(data.scalar_type() == at::kByte && data.numel() == x.numel() && data.is_contiguous());
+  TORCH_CHECK(scale.scalar_type() == at::kByte && scale.numel() == x.numel() / 32 && scale.is_contiguous());
+  ddpt::launch_quantize_mxfp8(x.data_ptr(), x.scalar_type() == at::kFloat, data.data_ptr<uint8_t>(),
+                              scale.data_ptr<uint8_t>(), rows, (int)cols, cur());
+  return {data, scale};
+}
+
+int64_t conv_gemm_mxfp8(at::Tensor a, at::Tensor a_scale, at::Tensor b, at::Tensor b_scale, at::Tensor out,
+                        std::vector<int64_t> out_nhw, std::vector<int64_t> box_nhw, std::vector<int64_t> taps_hw,
+                        c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> stat_partials) {
+  need(a, at::kByte, "a"); need(a_scale, at::kByte, "a_scale"); need(b, at::kByte, "b"); need(b_scale, at::kByte, "b_scale");
+  need(out, at::kBFloat16, "out");
+  TORCH_CHECK(a.dim() == 4 && b.dim() == 2 && out.dim() == 2);
+  c10::cuda::CUDAGuard g(a.device());
+  ddpt::Mxfp8GemmProblem p{};
+  p.a = a.data_ptr<uint8_t>(); p.a_scale = a_scale.data_ptr<uint8_t>();
+  p.a_n = (int)a.size(0); p.a_h = (int)a.size(1); p.a_w = (int)a.size(2); p.a_c = (int)a.size(3);
+  p.out_n = (int)out_nhw[0]; p.out_h = (int)out_nhw[1]; p.out_w = (int)out_nhw[2];
+  p.box_n = (int)box_nhw[0]; p.box_h = (int)box_nhw[1]; p.box_w = (int)box_nhw[2];
+  p.taps_h = (int)taps_hw[0]; p.taps_w = (int)taps_hw[1];
+  const int64_t taps = p.taps_h * p.taps_w;
+  TORCH_CHECK(a_scale.numel() == a.numel() / 32 && b.size(1) == taps * p.a_c && b_scale.numel() == b.numel() / 32);
+  p.b = b.data_ptr<uint8_t>(); p.b_scale = b_scale.data_ptr<uint8_t>(); p.n_total = (int)b.size(0);
+  TORCH_CHECK(out.size(0) >= (int64_t)p.out_n * p.out_h * p.out_w && out.size(1) >= p.n_total);
+  p.out = out.data_ptr(); p.ld_out = out.stride(0);
+  if (bias.has_value()) { need(*bias, at::kFloat, "bias"); p.bias = bias->data_ptr<float>(); }
+  p.relu = relu;
+  if (stat_partials.has_value()) {
+    need(*stat_partials, at::kFloat, "stat_partials");
+    const int64_t tiles = (int64_t)((p.out_w + p.box_w - 1) / p.box_w) * ((p.out_h + p.box_h - 1) / p.box_h) *
+                          ((p.out_n + p.box_n - 1) / p.box_n);
+    const int64_t groups = std::max<int64_t>(tiles, std::min<int64_t>(tiles * (p.n_total / 128),
+                                             at::cuda::getCurrentDeviceProperties()->multiProcessorCount));
+    TORCH_CHECK(stat_partials->numel() >= groups * 8 * p.n_total, "stat_partials too small");
+    p.stat_partials = stat_partials->data_ptr<float>();
+  }
+  return ddpt::launch_conv_gemm_mxfp8(p, cur());
+}
+
 }  // namespace
 
 void ddpt_bind_nn(pybind11::module_& m) {
+  m.def("quantize_mxfp8", &quantize_mxfp8);
+  m.def("conv_gemm_mxfp8", &conv_gemm_mxfp8);
   m.def("conv0_partial_rows", &conv0_partial_rows);
   m.def("bn_bwd_partial_rows", &bn_bwd_partial_rows);
   m.def("conv0_fwd", &conv0_fwd);

@@ -100,7 +100,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const uint32_t tx_bytes = args.a_rows_bytes + kBStageBytes;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kStages;
@@ -125,7 +125,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kStages;
         const uint32_t phase = (i / kStages) & 1;

@@ -103,7 +103,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp == 0) {
     // ===== TMA producer: one halo brick per (tile, channel chunk); weights resident or streamed per tap =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       if (B_RES) {
         mbar_arrive_expect_tx(b_ready, static_cast<uint32_t>(total_kb) * kBStageBytes);
         for (int tap = 0; tap < num_taps; ++tap)
@@ -140,7 +140,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp == 1) {
     // ===== MMA issuer: every tap is a shifted view of the halo brick =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       uint32_t ia = 0, ib = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 45);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {

@@ -101,7 +101,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const uint32_t tx_bytes = args.a_rows_bytes + (B_RES ? 0 : kBStageBytes);
       if (B_RES) {                                         // one-time: every (tap, chunk) weight tile, column block 0
         mbar_arrive_expect_tx(b_ready, static_cast<uint32_t>(total_kb) * kBStageBytes);
@@ -150,7 +150,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       uint32_t it = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 5);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {

@@ -85,7 +85,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const uint32_t tx_bytes = (kABlocks + kBBlocks) * args.brick_rows * 128;
       for (int i = 0; i < num_bricks; ++i) {
         const int s = i % args.stages;
@@ -108,7 +108,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const int k_steps = args.brick_rows / kUmmaK;
       for (int i = 0; i < num_bricks; ++i) {
         const int s = i % args.stages;

@@ -100,7 +100,7 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
 
   if (warp == 0) {
     // ===== TMA producer: dY brick + X halo brick per reduction step =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const CUtensorMap* tmx = grp.map == 0 ? &tmap_x0 : &tmap_x1;
       const uint32_t tx_bytes = (kABlocks * args.brick_rows + kBBlocks * grp.halo_rows) * 128;
       for (int i = 0; i < num_bricks; ++i) {
@@ -126,7 +126,7 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one chain per tap, B = shifted view of the halo tile =====
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const int k_steps = args.brick_rows / kUmmaK;
       const int gpr = args.box_w / 8;                      // 8-pixel K groups per (h, n) row of the brick
       const int xw = args.box_w + grp.ns - 1;              // halo row width in pixels

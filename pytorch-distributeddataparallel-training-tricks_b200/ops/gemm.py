@@ -251,3 +251,39 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] 
     res = conv_wgrad(dy.view(1, 1, m, n), x.view(1, 1, m, k), 1, 1,
                      None if out is None else out.view(n, 1, 1, k), split_k, accumulate, None, multitap)
     return res.view(n, k)
+
+
+# ---- block-scaled fp8 (MXFP8) forward path ------------------------------------------------------------------------
+def quantize_mxfp8(x: torch.Tensor, data_out: Optional[torch.Tensor] = None, scale_out: Optional[torch.Tensor] = None):
+    """e4m3 payload (uint8) + one UE8M0 scale per 32 elements of the last dimension (csrc/amp/quantize_mxfp8.cu)."""
+    return require_native().quantize_mxfp8(x.contiguous(), data_out, scale_out)
+
+
+def dequantize_mxfp8(data: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """fp32 values of an MXFP8 tensor (reference / tests)."""
+    vals = data.view(torch.float8_e4m3fn).float()
+    s = torch.pow(2.0, scale.float() - 127.0)
+    return (vals.view(*scale.shape, 32) * s.unsqueeze(-1)).view(data.shape)
+
+
+def conv_fwd_mxfp8(xq: torch.Tensor, xs: torch.Tensor, wq: torch.Tensor, ws: torch.Tensor, kh: int, kw: int,
+                   bias: Optional[torch.Tensor] = None, relu: bool = False,
+                   stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """'valid' stride-1 convolution on MXFP8 operands (tcgen05.mma.kind::mxf8f6f4.block_scale), bf16 output."""
+    ext = require_native()
+    n, h, w, c = xq.shape
+    ho, wo = h - kh + 1, w - kw + 1
+    c_out = wq.shape[0]
+    if out is None:
+        out = torch.empty((n, ho, wo, c_out), dtype=torch.bfloat16, device=xq.device)
+    box = pick_box(n, ho, wo)
+    tiles = ext.conv_gemm_mxfp8(xq, xs, wq, ws, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], bias, relu,
+                                stat_partials)
+    return out, tiles
+
+
+def linear_fwd_mxfp8(xq, xs, wq, ws, bias=None, relu=False, stat_partials=None, out=None):
+    m, k = xq.shape
+    y, tiles = conv_fwd_mxfp8(xq.view(1, 1, m, k), xs.view(1, 1, m, k // 32), wq, ws, 1, 1, bias, relu, stat_partials,
+                              None if out is None else out.view(1, 1, m, wq.shape[0]))
+    return y.view(m, wq.shape[0]), tiles

@@ -230,3 +230,54 @@ def test_fused_lookahead_sgd_matches_eager(ext):
     torch.testing.assert_close(fused.shadow.float(), fused.arena.param_arena, rtol=1e-2, atol=1e-3)
     sd = oa.state_dict()
     assert len(sd["slow_state"]) == 4 and len(sd["fast_state"]) == 4
+
+
+# ---------------------------------------------------------------------------------------------
+# block-scaled fp8 (MXFP8)
+# ---------------------------------------------------------------------------------------------
+def test_quantize_mxfp8_roundtrip(ext):
+    from ddpt_b200.ops import gemm
+    x = (torch.randn(64, 256, device="cuda") * torch.logspace(-3, 2, 64, device="cuda").unsqueeze(1)).bfloat16()
+    x[3, 32:64] = 0
+    q, s = gemm.quantize_mxfp8(x)
+    assert q.dtype == torch.uint8 and q.shape == x.shape and s.shape == (64, 8)
+    back = gemm.dequantize_mxfp8(q, s)
+    blocks = x.float().view(64, 8, 32)
+    amax = blocks.abs().amax(-1)
+    # scale is the smallest power of two that maps the block into e4m3 range; error <= half an e4m3 ulp of amax
+    pow2 = torch.pow(2.0, s.float() - 127.0)
+    assert torch.all(amax <= 448.0 * pow2 * 1.0001) and torch.all((amax > 224.0 * pow2) | (amax == 0))
+    err = (back.view(64, 8, 32) - blocks).abs().amax(-1)
+    assert torch.all(err <= amax * 2.0 ** -4 + 1e-30)
+    assert torch.all(back[3, 32:64] == 0)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1024, 512, 8192), (304, 256, 512)])
+def test_linear_fwd_mxfp8_matches_dequantized_reference(ext, m, n, k):
+    from ddpt_b200.ops import gemm
+    x = _bf16(m, k, seed=21)
+    w = _bf16(n, k, scale=k ** -0.5, seed=22)
+    xq, xs = gemm.quantize_mxfp8(x)
+    wq, ws = gemm.quantize_mxfp8(w)
+    bias = torch.randn(n, device="cuda")
+    y, _ = gemm.linear_fwd_mxfp8(xq, xs, wq, ws, bias)
+    want = gemm.dequantize_mxfp8(xq, xs) @ gemm.dequantize_mxfp8(wq, ws).t() + bias
+    assert _rel_err(y, want) < 6e-3                      # bf16 output rounding only
+    assert _rel_err(y, x.float() @ w.float().t() + bias) < 6e-2   # and close to the unquantised product
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(6, 12, 12, 128, 256), (4, 10, 10, 256, 512)])
+def test_conv3x3_fwd_mxfp8(ext, n, h, w, ci, co):
+    from ddpt_b200.ops import gemm
+    x = _bf16(n, h, w, ci, seed=23)
+    wk = _bf16(co, 9 * ci, scale=(9 * ci) ** -0.5, seed=24)
+    xq, xs = gemm.quantize_mxfp8(x)
+    wq, ws = gemm.quantize_mxfp8(wk)
+    groups = gemm.stat_row_groups(n, h - 2, w - 2, co, 128)
+    stats = torch.zeros(groups * 8 * co, device="cuda")
+    y, _ = gemm.conv_fwd_mxfp8(xq, xs, wq, ws, 3, 3, None, False, stats)
+    want = _conv_ref(gemm.dequantize_mxfp8(xq, xs), gemm.dequantize_mxfp8(wq, ws), co, ci)
+    assert _rel_err(y.permute(0, 3, 1, 2), want) < 6e-3
+    part = stats.view(groups * 4, 2, co).sum(0)
+    flat = want.permute(0, 2, 3, 1).reshape(-1, co)
+    torch.testing.assert_close(part[0], flat.sum(0), rtol=2e-3, atol=5e-2 * math.sqrt(flat.shape[0]))
