@@ -186,10 +186,11 @@ def _slab(device, numel: int) -> torch.Tensor:
 
 
 def use_multitap(flag: Optional[bool] = None) -> bool:
-    """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu); DDPT_WGRAD_MULTITAP=0 disables."""
+    """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu).  Off by default: on B200 the
+    one-tap-per-CTA kernel measures faster end to end (2.13 vs 2.22 ms/step, profiles/); DDPT_WGRAD_MULTITAP=1 enables."""
     if flag is not None:
         return flag
-    return os.environ.get("DDPT_WGRAD_MULTITAP", "1") != "0"
+    return os.environ.get("DDPT_WGRAD_MULTITAP", "0") == "1"
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
@@ -199,6 +200,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
     ext = require_native()
     n, ho, wo, c_out = dy.shape
     c_in = x.shape[3]
+    if block_n is None and c_in % 128 == 0 and kh * kw > 1:
+        block_n = 128            # measured: 128-wide accumulators beat 256 for the pixel-reduction GEMM (conv.10)
     bn = _block_n(c_in, block_n)
     mt = use_multitap(multitap)
     bricks_of = lambda b: -(-wo // b[2]) * -(-ho // b[1]) * -(-n // b[0])

@@ -49,8 +49,9 @@ class _Workspace:
         # statistic partial rows: conv epilogues write 4 rows (warp quadrants) per M tile
         groups = gemm.stat_row_groups
         rows = [ext.conv0_partial_rows(), 4 * groups(batch, 24, 24, 128, None, device),
-                4 * groups(batch, 10, 10, 256, None, device), 4 * groups(batch, 8, 8, 512, None, device),
-                4 * groups(1, 1, batch, 512, 64, device)]
+                4 * max(groups(batch, 10, 10, 256, None, device), groups(batch, 10, 10, 256, 128, device)),
+                4 * max(groups(batch, 8, 8, 512, None, device), groups(batch, 8, 8, 512, 128, device)),
+                4 * max(groups(1, 1, batch, 512, 64, device), groups(1, 1, batch, 512, 128, device))]
         chans = (64, 128, 256, 512, 512)
         self.part = torch.zeros(max(max(r * 2 * c for r, c in zip(rows, chans)),
                                     ext.bn_bwd_partial_rows() * 2 * 512), dtype=f32, device=device)
@@ -60,6 +61,15 @@ class _Workspace:
         self.da = [e(batch, 26, 26, 64), e(batch, 12, 12, 128), e(batch, 10, 10, 256), e(batch, 8192),
                    e(batch, 512)]
         self.saved_x: Optional[torch.Tensor] = None
+        # block-scaled fp8 copies of the activations feeding conv.7, conv.10 and dense.1 ("O1-fp8")
+        self.q = {}
+
+    def fp8_buffers(self, k: int, like: torch.Tensor):
+        if k not in self.q:
+            u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=like.device)
+            shape = list(like.shape)
+            self.q[k] = (u8(*shape), u8(*shape[:-1], shape[-1] // 32))
+        return self.q[k]
 
 
 class FusedToyNet:
@@ -74,6 +84,7 @@ class FusedToyNet:
         self.bn = [model.conv[1], model.conv[4], model.conv[8], model.conv[11], model.dense[2]]
         self._ws: Dict[int, _Workspace] = {}
         self._shadow_cache: Dict[int, tuple] = {}
+        self._w_fp8: Dict[int, tuple] = {}
         self._staging: Optional[torch.Tensor] = None
         self.launches = 0
 
@@ -106,6 +117,16 @@ class FusedToyNet:
         w = src.reshape(p.shape[0], -1).to(torch.bfloat16).contiguous()
         self._shadow_cache[pidx] = (key, w)
         return w
+
+    def _weight_fp8(self, pidx: int):
+        """MXFP8 copy (e4m3 + UE8M0 per 32 along K) of a weight matrix, re-quantised from the bf16 shadow."""
+        w = self._weight_bf16(pidx)
+        if pidx not in self._w_fp8:
+            self._w_fp8[pidx] = (torch.empty(w.shape, dtype=torch.uint8, device=w.device),
+                                 torch.empty((w.shape[0], w.shape[1] // 32), dtype=torch.uint8, device=w.device))
+        q, sc = self._w_fp8[pidx]
+        self.ext.quantize_mxfp8(w, q, sc)
+        return q, sc
 
     def _grad_view(self, flat: torch.Tensor, offset: int, p: torch.Tensor) -> torch.Tensor:
         v = flat[offset: offset + p.numel()]
@@ -160,14 +181,26 @@ class FusedToyNet:
         act = ws.a[0]
         for k, (pidx, h_in, c_in, c_out, pool) in enumerate(_TC_BLOCKS, start=1):
             h_out = h_in - 2
-            _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
+            if self.compute == "fp8" and c_in % 128 == 0:
+                xq, xs = ws.fp8_buffers(k, act)
+                ext.quantize_mxfp8(act, xq, xs)
+                wq, wsc = self._weight_fp8(pidx)
+                _, tiles = gemm.conv_fwd_mxfp8(xq, xs, wq, wsc, 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
+            else:
+                _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
             self._bn_coeffs(k, ws, train, 4 * tiles, batch * float(h_out * h_out))
             ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, k == 3)
             act = ws.a[k]
         # dense.1 + BN1d + ReLU
         y4 = ws.y[4].view(batch, 512)
-        _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(), False,
-                                 part, y4.view(1, 1, batch, 512), block_n=64)
+        if self.compute == "fp8":
+            xq, xs = ws.fp8_buffers(4, ws.a[3])
+            ext.quantize_mxfp8(ws.a[3], xq, xs)
+            wq, wsc = self._weight_fp8(16)
+            _, tiles = gemm.linear_fwd_mxfp8(xq, xs, wq, wsc, P[17].detach(), False, part, y4)
+        else:
+            _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(),
+                                     False, part, y4.view(1, 1, batch, 512), block_n=64)
         self._bn_coeffs(4, ws, train, 4 * tiles, float(batch))
         ext.bn_relu_pool(ws.y[4], ws.coef[4], ws.a[4], False, False)
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)

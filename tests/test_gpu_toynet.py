@@ -171,3 +171,32 @@ def test_engine_overflow_skips_step_and_halves_scale():
     assert sd["scale"] == 32768.0 and sd["skipped"] == 1
     assert fo.state.tolist()[5] == 1 and fo.state.tolist()[0] == 3
     amp.reset()
+
+
+def test_fp8_block_scaled_forward_path_trains():
+    """opt_level O1-fp8: conv.7 / conv.10 / dense.1 forward on MXFP8 tensor cores; loss still falls."""
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.data import BatchLoader, synthetic_mnist
+    from ddpt_b200.engine import iterate_loader
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.utils import same_seeds
+    amp.reset()
+    same_seeds(5)
+    model = Toy_Net().cuda()
+    ref = copy.deepcopy(model)
+    opt = Lookahead(SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+    model, opt = amp.initialize(model, optimizers=opt, opt_level="O1-fp8")
+    assert model._fused.compute == "fp8"
+    x, _ = _batch(128, seed=9)
+    model.train(); ref.train()
+    with torch.no_grad():
+        assert _rel(model(x), ref.forward_reference(x)) < 0.12      # e4m3 operands on three layers
+    loss_fn = nn.CrossEntropyLoss()
+    assert ops.attach_step_engine(model, loss_fn, opt)
+    data = synthetic_mnist(2048, seed=1)
+    loader = BatchLoader(data, 256, None, torch.device("cuda"), mode="device")
+    loader.quiet = True
+    hist = [iterate_loader(loader, model, loss_fn, 0, opt, training=True)[0] for _ in range(3)]
+    assert hist[-1] < hist[0] * 0.75, hist
+    amp.reset()
