@@ -138,19 +138,35 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t x_addr = a_addr + kABlocks * args.slot_a;
-        int acc_idx = 0;
-        for (int t = 0; t < box_taps; ++t) {
-          if (!((grp.mask >> t) & 1)) continue;
-          const int dr = t / grp.ns, ds = t - dr * grp.ns;
-          const uint32_t tmem_d = tmem_base + acc_idx * BN;
-          ++acc_idx;
+        if (BN == 64 && grp.ns == 1 && box_taps > 1 && grp.mask == (1 << box_taps) - 1) {
+          // The taps of a filter column are consecutive 64-wide N blocks of ONE wide MMA: tap dr's view of the X
+          // brick starts box_n * xw rows after tap dr-1's, which is exactly the descriptor's leading-dimension
+          // stride.  N = taps * 64 (<= 256) amortises the A-operand fetch and the issue slot over all taps.
+          const uint32_t idesc_wide = make_idesc_bf16(kBlockM, BN * box_taps, true, true);
+          const uint32_t tap_pitch = args.box_n * xw * 128;
           for (int k = 0; k < k_steps; ++k) {
-            const int g0 = 2 * k;                           // first of the two 8-pixel K groups of this step
-            const int row = g0 / gpr, cg = g0 - row * gpr;  // (h, n) row of the brick, 8-pixel column group
-            const uint32_t x_off = ((row + dr * args.box_n) * xw + cg * 8 + ds) * 128;
+            const int g0 = 2 * k;
+            const int row = g0 / gpr, cg = g0 - row * gpr;
+            const uint32_t x_off = (row * xw + cg * 8) * 128;
             const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
-            const uint64_t bdesc = make_smem_desc(x_addr + x_off, args.slot_x, sbo_x);
-            mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
+            const uint64_t bdesc = make_smem_desc(x_addr + x_off, tap_pitch, sbo_x);
+            mma_bf16_ss(tmem_base, adesc, bdesc, idesc_wide, (i | k) != 0 ? 1u : 0u);
+          }
+        } else {
+          int acc_idx = 0;
+          for (int t = 0; t < box_taps; ++t) {
+            if (!((grp.mask >> t) & 1)) continue;
+            const int dr = t / grp.ns, ds = t - dr * grp.ns;
+            const uint32_t tmem_d = tmem_base + acc_idx * BN;
+            ++acc_idx;
+            for (int k = 0; k < k_steps; ++k) {
+              const int g0 = 2 * k;                           // first of the two 8-pixel K groups of this step
+              const int row = g0 / gpr, cg = g0 - row * gpr;  // (h, n) row of the brick, 8-pixel column group
+              const uint32_t x_off = ((row + dr * args.box_n) * xw + cg * 8 + ds) * 128;
+              const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
+              const uint64_t bdesc = make_smem_desc(x_addr + x_off, args.slot_x, sbo_x);
+              mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
         }
         mma_commit(&empty_bar[s]);
