@@ -28,7 +28,7 @@ from ..data import make_loaders
 from ..models import Toy_Net, resnet50
 from ..optim import SGD, LambdaLR, Lookahead, ReduceLROnPlateau, warmup_lambda
 from ..parallel import DistributedDataParallel
-from ..utils import EarlyStopping, ScalarLogger, same_seeds, save_weights
+from ..utils import CudaStepTimer, EarlyStopping, ScalarLogger, nvtx_range, same_seeds, save_weights
 from ..utils.checkpoint import load_resume_state, save_resume_state
 from .process import iterate_loader
 
@@ -108,18 +108,21 @@ def train(args) -> dict:
 
     tb = ScalarLogger(os.path.join(args.model_path, "logs", args.exp_name)) if is_main else None
     history = []
+    profile = getattr(args, "profile", False)
+    train_timer, valid_timer = CudaStepTimer(), CudaStepTimer()      # device-side epoch timing (--profile)
     try:
         for epoch in range(start_epoch, args.epochs):
             t0 = time.time()
             train_sampler.set_epoch(epoch)
 
             parallel_model.train()
-            train_loss, train_acc, curr_lr = iterate_loader(
-                loader=train_loader, model=parallel_model, loss_function=loss_function,
-                local_rank=args.local_rank, apex_optimizer=apex_optimizer, training=True)
+            with nvtx_range(f"train/epoch{epoch}", profile), train_timer.region():
+                train_loss, train_acc, curr_lr = iterate_loader(
+                    loader=train_loader, model=parallel_model, loss_function=loss_function,
+                    local_rank=args.local_rank, apex_optimizer=apex_optimizer, training=True)
 
             parallel_model.eval()
-            with torch.no_grad():
+            with torch.no_grad(), nvtx_range(f"valid/epoch{epoch}", profile), valid_timer.region():
                 valid_loss, valid_acc = iterate_loader(
                     loader=valid_loader, model=parallel_model, loss_function=loss_function,
                     local_rank=args.local_rank, apex_optimizer=None, training=False)
@@ -158,5 +161,13 @@ def train(args) -> dict:
     finally:
         if tb is not None:
             tb.close()
+    if profile and is_main and device.type == "cuda":
+        steps = len(train_loader)
+        t = train_timer.summary()
+        if t.get("n"):
+            print(f"[profile] train pass: median {t['median_ms']:.2f} ms device time = "
+                  f"{t['median_ms'] / max(steps, 1):.3f} ms/step, "
+                  f"{steps * args.batch_size / t['median_ms'] * 1e3:.0f} images/s/GPU; "
+                  f"valid pass median {valid_timer.summary().get('median_ms', float('nan')):.2f} ms")
     return {"history": history, "best_valid_acc": best_valid_acc, "model": parallel_model,
             "optimizer": apex_optimizer}
