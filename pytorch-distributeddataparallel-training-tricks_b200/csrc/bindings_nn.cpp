@@ -107,7 +107,8 @@ void bn_bwd_finalize(at::Tensor partials, int64_t num_partials, double count, at
   TORCH_CHECK(bwd_coef.numel() >= 3 * c && dgamma.numel() == c && dbeta.numel() == c);
   c10::cuda::CUDAGuard guard(gamma.device());
   ddpt::launch_bn_bwd_finalize(partials.data_ptr<float>(), (int)num_partials, c, count, gamma.data_ptr<float>(),
-                               coeffs.data_ptr<float>() + 3 * c, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                               coeffs.data_ptr<float>() + 2 * c, coeffs.data_ptr<float>() + 3 * c, dgamma.data_ptr<float>(),
+                               dbeta.data_ptr<float>(),
                                bwd_coef.data_ptr<float>(), accumulate, cur());
 }
 

@@ -40,7 +40,7 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
                          int h, int w, int c, int pool, int flatten_chw, cudaStream_t s);
 
 // ---- BatchNorm backward (two passes) ----------------------------------------------------------------------
-// Pass 1: partials[blk][0][c] = sum dz, partials[blk][1][c] = sum dz * xhat, with dz = grad of the BN output
+// Pass 1: partials[blk][0][c] = sum dz, partials[blk][1][c] = sum dz * y (finalize converts to sum dz * xhat), dz = grad of the BN output
 // after routing g through max-pool (if any) and the ReLU mask.  Returns the number of partial rows.
 int bn_bwd_partial_rows();
 int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
@@ -49,8 +49,8 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 // Fold pass-1 partials: dgamma = sum dz*xhat, dbeta = sum dz (written/accumulated into the grad arena) and the
 // three per-channel coefficients of pass 2.
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
-                            const float* invstd, float* dgamma, float* dbeta, float* coef /*[3][C]*/,
-                            int accumulate, cudaStream_t s);
+                            const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                            float* coef /*[3][C]*/, int accumulate, cudaStream_t s);
 // Pass 2: dy = c1 * (dz - c2 - xhat * c3) as bf16 NHWC; optionally sum dy per channel (conv bias gradient).
 void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
                          const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy,

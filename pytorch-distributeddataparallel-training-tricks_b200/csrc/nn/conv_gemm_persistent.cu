@@ -20,6 +20,7 @@
 #include "../include/ddpt_common.cuh"
 #include "../include/umma.cuh"
 #include "tensor_map.h"
+#include <algorithm>
 #include <stdexcept>
 
 namespace ddpt {
@@ -48,6 +49,8 @@ struct KernelArgs {
   const float* bias;
   float* stat_partials;
   int relu, out_fp32, a_rows_bytes;
+  int stages;                   // pipeline depth (stage = kbs K blocks of A [+ B unless resident])
+  int kbs;                      // K blocks (tap x 64-channel chunk) per pipeline stage: amortises the barrier round trip
 };
 
 
@@ -58,8 +61,7 @@ template <int BN, bool B_MN, bool B_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
-  constexpr int kStages = B_RES ? 4 : stages_for<BN>();
-  constexpr int kBStageBytes = BN * kBlockK * 2;
+  constexpr int kBStageBytes = BN * kBlockK * 2;            // one K block of B
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
 
@@ -67,12 +69,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int total_kb = args.num_taps * args.k_chunks;
+  const int kStages = args.stages, kbs = args.kbs;
+  const int steps_per_tile = (total_kb + kbs - 1) / kbs;   // pipeline steps (barrier round trips) per tile
+  const int a_stage_bytes = kbs * kAStageBytes;
+  const int b_stage_bytes = kbs * kBStageBytes;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kAStageBytes;         // B_RES: total_kb resident tiles, else kStages ring slots
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (B_RES ? total_kb : kStages) * kBStageBytes);
+  uint8_t* smem_b = smem + kStages * a_stage_bytes;        // B_RES: total_kb resident tiles, else kStages ring slots
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (B_RES ? total_kb * kBStageBytes : kStages * b_stage_bytes));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;               // [2]
   uint64_t* tmem_empty = tmem_full + 2;                    // [2]
@@ -125,25 +131,30 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.box_w, h0 = th * args.box_h, n0 = tn * args.box_n;
         const int col0 = tile_n * BN;
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+        for (int step = 0; step < steps_per_tile; ++step, ++it) {
           const int s = it % kStages;
           const uint32_t phase = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1, 1);
-          const int tap = kb / args.k_chunks;
-          const int chunk = kb - tap * args.k_chunks;
-          const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_4d(smem_a + s * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
-                      w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
-          if (B_RES) {
-            // weights are resident
-          } else if (!B_MN) {
-            tma_load_2d(smem_b + s * kBStageBytes, &tmap_b, &full_bar[s], kb * kBlockK, col0);
-          } else {
+          const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * tx_bytes);
+          for (int j = 0; j < nkb; ++j) {
+            const int kb = kb0 + j;
+            const int tap = kb / args.k_chunks;
+            const int chunk = kb - tap * args.k_chunks;
+            const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
+            tma_load_4d(smem_a + s * a_stage_bytes + j * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
+                        w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
+            uint8_t* b_dst = smem_b + s * b_stage_bytes + j * kBStageBytes;
+            if (B_RES) {
+              // weights are resident
+            } else if (!B_MN) {
+              tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(smem_b + s * kBStageBytes + j * (kBlockK * 128), &tmap_b, &full_bar[s],
-                          tap * args.n_total + col0 + j * 64, chunk * kBlockK);
+              for (int jj = 0; jj < BN / 64; ++jj)
+                tma_load_2d(b_dst + jj * (kBlockK * 128), &tmap_b, &full_bar[s],
+                            tap * args.n_total + col0 + jj * 64, chunk * kBlockK);
+            }
           }
         }
       }
@@ -158,19 +169,24 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+        for (int step = 0; step < steps_per_tile; ++step, ++it) {
           const int s = it % kStages;
           const uint32_t phase = (it / kStages) & 1;
           mbar_wait(&full_bar[s], phase, 2);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + s * kAStageBytes);
-          const uint32_t b_addr = smem_u32(smem_b + (B_RES ? kb : s) * kBStageBytes);
+          const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);
+          for (int j = 0; j < nkb; ++j) {
+            const int kb = kb0 + j;
+            const uint32_t a_addr = smem_u32(smem_a + s * a_stage_bytes + j * kAStageBytes);
+            const uint32_t b_addr = B_RES ? smem_u32(smem_b + kb * kBStageBytes)
+                                          : smem_u32(smem_b + s * b_stage_bytes + j * kBStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
-                                        : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
-            mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
+              const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
+                                          : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
+              mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           mma_commit(&empty_bar[s]);
         }
@@ -293,13 +309,27 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 
 template <int BN, bool B_MN, bool B_RES>
 int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
-  constexpr int kStages = B_RES ? 4 : stages_for<BN>();
   constexpr int kBStageBytes = BN * kBlockK * 2;
   const int total_kb_host = p.taps_h * p.taps_w * (p.a_c / kBlockK);
-  const size_t smem_bytes = 1024 + kStages * kAStageBytes + (size_t)(B_RES ? total_kb_host : kStages) * kBStageBytes +
-                            (2 * kStages + 5) * 8 + 16;
+  // K blocks per pipeline stage: a barrier round trip (try_wait + fence + commit, ~300 cycles) should be covered by
+  // >= ~512 tensor cycles of MMAs; one K block is 4 x (BN/4) cycles.  ncu on conv.3 dgrad (N = 64, one K block per
+  // stage) showed the tensor pipe only 24 % active with every queue shallow (profiles/ncu_dgrad3.txt).
+  int kbs = BN >= 256 ? 1 : (BN == 128 ? 2 : 3);
+  if (kbs > total_kb_host) kbs = total_kb_host;
+  const size_t budget = 227 * 1024 - 2048;
+  const size_t resident_bytes = B_RES ? (size_t)total_kb_host * kBStageBytes : 0;
+  const size_t stage_bytes = (size_t)kbs * (kAStageBytes + (B_RES ? 0 : kBStageBytes));
+  int stages = (int)std::min<size_t>(8, (budget - resident_bytes) / stage_bytes);
+  while (stages < 2 && kbs > 1) {           // keep at least two stages (>= 4 K blocks) in flight
+    --kbs;
+    stages = (int)std::min<size_t>(8, (budget - resident_bytes) / ((size_t)kbs * (kAStageBytes + (B_RES ? 0 : kBStageBytes))));
+  }
+  if (stages < 2) throw std::runtime_error("conv_gemm (persistent): tile does not fit shared memory");
+  const size_t smem_bytes = 1024 + (size_t)stages * kbs * (kAStageBytes + (B_RES ? 0 : kBStageBytes)) + resident_bytes +
+                            (2 * stages + 5) * 8 + 16;
 
   KernelArgs a{};
+  a.stages = stages; a.kbs = kbs;
   a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
   a.out_w = p.out_w; a.out_h = p.out_h; a.out_n = p.out_n;
   a.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;

@@ -338,16 +338,16 @@ __device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, i
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
   extern __shared__ float s_part[];                       // [2][c]
   const int cv = k.c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
   const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
   const long long total_pix = (long long)k.n * oh * ow;
-  float sc[8], sh[8], mu[8], is[8], s_dz[8], s_dzx[8];
+  // row 1 of the partials holds sum(dz * y); bn_bwd_finalize turns it into sum(dz * xhat) = invstd * (sum(dz*y) - mean*sum(dz))
+  float sc[8], sh[8], s_dz[8], s_dzx[8];
   load8f(k.scale + v * 8, sc); load8f(k.shift + v * 8, sh);
-  load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_dz[j] = s_dzx[j] = 0.f;
   const long long stride = (long long)gridDim.x * rows_per_blk;
@@ -374,51 +374,58 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
           const float z = fmaf(f[j], sc[j], sh[j]);
           const float dz = z > 0.f ? g[j] : 0.f;
           s_dz[j] += dz;
-          s_dzx[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s_dzx[j]);
+          s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
         }
       }
     }
-  } else
-  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
-    const int pw = (int)(pix % ow);
-    const int ph = (int)((pix / ow) % oh);
-    const long long img = pix / ((long long)ow * oh);
-    float g[8];
-    load_g(k, img, ph, pw, oh, ow, v, g);
-    if (!POOL) {
-      float f[8];
-      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(f[j], sc[j], sh[j]);
-        const float dz = z > 0.f ? g[j] : 0.f;
-        s_dz[j] += dz;
-        s_dzx[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s_dzx[j]);
-      }
-    } else {
-      const __nv_bfloat16* base = k.y + ((img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
-      float best[8], besty[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }     // z <= 0 everywhere -> no gradient
-      uint4 yq[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) yq[q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
+  } else {
+    // (pooled / flattened layouts) walk output positions with incremental 32-bit (pw, ph, img) updates: no
+    // 64-bit divisions in the loop -- they were ~40 % of this kernel's issue slots (profiles/ncu_bnreduce.txt)
+    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
+    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
+    int pw = (int)(first % ow), ph = (int)((first / ow) % oh), img = (int)(first / ((unsigned)ow * oh));
+    const int d_pw = (int)(stride32 % ow), d_ph = (int)((stride32 / ow) % oh), d_img = (int)(stride32 / ((unsigned)ow * oh));
+    for (unsigned pix = first; pix < total32; pix += stride32) {
+      float g[8];
+      load_g(k, img, ph, pw, oh, ow, v, g);
+      if (!POOL) {
         float f[8];
-        unpack8(yq[q], f);
+        unpack8(ldg16(k.y + (size_t)pix * k.c + v * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[j], sc[j], sh[j]);
-          if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
+          const float dz = z > 0.f ? g[j] : 0.f;
+          s_dz[j] += dz;
+          s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
+        }
+      } else {
+        const __nv_bfloat16* base = k.y + (((size_t)img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
+        float best[8], besty[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }     // z <= 0 everywhere -> no gradient
+        uint4 yq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yq[q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack8(yq[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(f[j], sc[j], sh[j]);
+            if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dz = best[j] > 0.f ? g[j] : 0.f;
+          s_dz[j] += dz;
+          s_dzx[j] = fmaf(dz, besty[j], s_dzx[j]);
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dz = best[j] > 0.f ? g[j] : 0.f;
-        s_dz[j] += dz;
-        s_dzx[j] = fmaf(dz, (besty[j] - mu[j]) * is[j], s_dzx[j]);
-      }
+      pw += d_pw; if (pw >= ow) { pw -= ow; ++ph; }
+      ph += d_ph; if (ph >= oh) { ph -= oh; ++img; }
+      img += d_img;
     }
   }
   for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) s_part[i] = 0.f;
@@ -434,9 +441,9 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
 
 __global__ void __launch_bounds__(32 * kFinGroups)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
-                       const float* __restrict__ gamma, const float* __restrict__ invstd,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
-                       int accumulate) {
+                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       float* __restrict__ coef, int accumulate) {
   __shared__ double s_a[kFinGroups][32], s_b[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -466,6 +473,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
   __syncthreads();
   if (grp == 0 && c < channels) {
     for (int g = 1; g < kFinGroups; ++g) { a += s_a[g][lane]; b += s_b[g][lane]; }
+    b = (double)invstd[c] * (b - (double)mean[c] * a);        // sum(dz * y) -> sum(dz * xhat)
     if (accumulate) { dbeta[c] += (float)a; dgamma[c] += (float)b; }
     else { dbeta[c] = (float)a; dgamma[c] = (float)b; }
     coef[c] = gamma[c] * invstd[c];
@@ -475,7 +483,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                     float* __restrict__ dbias) {
   extern __shared__ float s_db[];                          // [c]
@@ -483,15 +491,24 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
   const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
   const long long total_pix = (long long)k.n * oh * ow;
-  float sc[8], sh[8], mu[8], is[8], c1[8], c2[8], c3[8], db[8];
+  // dy = c1 * (dz - c2 - xhat * c3), xhat = (y - mean) * invstd   ==>   dy = c1 * dz + k0 - k1 * y
+  float sc[8], sh[8], c1[8], k0[8], k1[8], db[8];
   load8f(k.scale + v * 8, sc); load8f(k.shift + v * 8, sh);
-  load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
-  load8f(coef + v * 8, c1); load8f(coef + k.c + v * 8, c2); load8f(coef + 2 * k.c + v * 8, c3);
+  load8f(coef + v * 8, c1);
+  {
+    float mu[8], is[8], c2[8], c3[8];
+    load8f(k.mean + v * 8, mu);  load8f(k.invstd + v * 8, is);
+    load8f(coef + k.c + v * 8, c2); load8f(coef + 2 * k.c + v * 8, c3);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) db[j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      k1[j] = c1[j] * is[j] * c3[j];
+      k0[j] = fmaf(k1[j], mu[j], -c1[j] * c2[j]);
+      db[j] = 0.f;
+    }
+  }
   const long long stride = (long long)gridDim.x * rows_per_blk;
   if (!POOL && !k.flatten) {
-    constexpr int U = 4;
+    constexpr int U = 2;
     for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
       uint4 yv[U], gv[U];
 #pragma unroll
@@ -513,60 +530,68 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[j], sc[j], sh[j]);
           const float dz = z > 0.f ? g[j] : 0.f;
-          o[j] = c1[j] * (dz - c2[j] - (f[j] - mu[j]) * is[j] * c3[j]);
+          o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
           db[j] += o[j];
         }
         *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
       }
     }
-  } else
-  for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
-    const int pw = (int)(pix % ow);
-    const int ph = (int)((pix / ow) % oh);
-    const long long img = pix / ((long long)ow * oh);
-    float g[8];
-    load_g(k, img, ph, pw, oh, ow, v, g);
-    if (!POOL) {
-      float f[8], o[8];
-      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(f[j], sc[j], sh[j]);
-        const float dz = z > 0.f ? g[j] : 0.f;
-        o[j] = c1[j] * (dz - c2[j] - (f[j] - mu[j]) * is[j] * c3[j]);
-        db[j] += o[j];
-      }
-      *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
-    } else {
-      const long long base_off = ((img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
-      uint4 yq[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) yq[q] = ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c);
-      float f[4][8];
-      float best[8];
-      int arg[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        unpack8(yq[q], f[q]);
+  } else {
+    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
+    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
+    int pw = (int)(first % ow), ph = (int)((first / ow) % oh), img = (int)(first / ((unsigned)ow * oh));
+    const int d_pw = (int)(stride32 % ow), d_ph = (int)((stride32 / ow) % oh), d_img = (int)(stride32 / ((unsigned)ow * oh));
+    for (unsigned pix = first; pix < total32; pix += stride32) {
+      float g[8];
+      load_g(k, img, ph, pw, oh, ow, v, g);
+      if (!POOL) {
+        float f[8], o[8];
+        unpack8(ldg16(k.y + (size_t)pix * k.c + v * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(f[q][j], sc[j], sh[j]);
-          if (z > best[j]) { best[j] = z; arg[j] = q; }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dz = arg[j] == q ? g[j] : 0.f;
-          o[j] = c1[j] * (dz - c2[j] - (f[q][j] - mu[j]) * is[j] * c3[j]);
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float dz = z > 0.f ? g[j] : 0.f;
+          o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
           db[j] += o[j];
         }
-        *reinterpret_cast<uint4*>(dy + base_off + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
+        *reinterpret_cast<uint4*>(dy + (size_t)pix * k.c + v * 8) = pack8(o);
+      } else {
+        const size_t base_off = (((size_t)img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
+        uint4 yq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yq[q] = ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c);
+        // pass A: arg-max of the window (only the winner index is kept; values are re-unpacked in pass B)
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack8(yq[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(f[j], sc[j], sh[j]);
+            if (z > best[j]) { best[j] = z; arg[j] = q; }
+          }
+        }
+        // pass B: dy for the four window positions
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8], o[8];
+          unpack8(yq[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dz = arg[j] == q ? g[j] : 0.f;
+            o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
+            db[j] += o[j];
+          }
+          *reinterpret_cast<uint4*>(dy + base_off + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
+        }
       }
+      pw += d_pw; if (pw >= ow) { pw -= ow; ++ph; }
+      ph += d_ph; if (ph >= oh) { ph -= oh; ++img; }
+      img += d_img;
     }
   }
   if (dbias == nullptr) return;
@@ -758,10 +783,10 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 }
 
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
-                            const float* invstd, float* dgamma, float* dbeta, float* coef, int accumulate,
-                            cudaStream_t s) {
+                            const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
+                            int accumulate, cudaStream_t s) {
   bn_bwd_finalize_kernel<<<(channels + 31) / 32, 32 * kFinGroups, 0, s>>>(partials, num_partials, channels, count, gamma,
-                                                                    invstd, dgamma, dbeta, coef, accumulate);
+                                                                    mean, invstd, dgamma, dbeta, coef, accumulate);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

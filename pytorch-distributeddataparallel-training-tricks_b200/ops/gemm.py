@@ -186,11 +186,13 @@ def _slab(device, numel: int) -> torch.Tensor:
 
 
 def use_multitap(flag: Optional[bool] = None) -> bool:
-    """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu).  Off by default: on B200 the
-    one-tap-per-CTA kernel measures faster end to end (2.13 vs 2.22 ms/step, profiles/); DDPT_WGRAD_MULTITAP=1 enables."""
+    """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu).  DDPT_WGRAD_MULTITAP=0/1 forces it off /
+    on; by default (None) the caller enables it only where it measured faster: C_in == 64, where a filter column's
+    three taps merge into one N = 192 MMA (2.06 vs 2.13 ms/step end to end)."""
     if flag is not None:
         return flag
-    return os.environ.get("DDPT_WGRAD_MULTITAP", "0") == "1"
+    env = os.environ.get("DDPT_WGRAD_MULTITAP")
+    return None if env is None else env == "1"
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
@@ -204,6 +206,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
         block_n = 128            # measured: 128-wide accumulators beat 256 for the pixel-reduction GEMM (conv.10)
     bn = _block_n(c_in, block_n)
     mt = use_multitap(multitap)
+    if mt is None:
+        mt = bn == 64 and kh * kw > 1
     bricks_of = lambda b: -(-wo // b[2]) * -(-ho // b[1]) * -(-n // b[0])
     sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
     slab = None
