@@ -110,7 +110,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           for (int chunk = 0; chunk < args.k_chunks; ++chunk)
             load_b(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes, b_ready, tap, chunk, 0);
       }
-      uint32_t ia = 0, ib = 0;
+      int a_s = 0, b_s = 0;
+      uint32_t a_phase = 0, b_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
         const int tw = tile_m % args.tiles_w;
@@ -118,18 +119,22 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * 8, h0 = th * args.box_h, n0 = tn * args.box_n;
         for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
-          for (int cs = 0; cs < args.taps_w; ++cs, ++ia) {       // one activation brick per filter column
-            const int sa = ia % args.a_stages;
-            mbar_wait(&a_empty[sa], ((ia / args.a_stages) & 1) ^ 1, 41);
+          for (int cs = 0; cs < args.taps_w; ++cs) {       // one activation brick per filter column
+            const int sa = a_s;
+            const uint32_t a_ph = a_phase;
+            if (++a_s == args.a_stages) { a_s = 0; a_phase ^= 1; }
+            mbar_wait(&a_empty[sa], a_ph ^ 1, 41);
             mbar_arrive_expect_tx(&a_full[sa], args.a_tile_bytes);
             tma_load_4d(smem_a + sa * args.a_slot_bytes, &tmap_a, &a_full[sa], chunk * kBlockK,
                         w0 + args.org_w_off + cs, n0, h0 + args.org_h_off);
             if (!B_RES) {
-              for (int dr = 0; dr < args.taps_h; ++dr, ++ib) {
+              for (int dr = 0; dr < args.taps_h; ++dr) {
                 const int r = args.tap_sign > 0 ? dr : args.taps_h - 1 - dr;
                 const int sx = args.tap_sign > 0 ? cs : args.taps_w - 1 - cs;
-                const int sb = ib % args.b_stages;
-                mbar_wait(&b_empty[sb], ((ib / args.b_stages) & 1) ^ 1, 42);
+                const int sb = b_s;
+                const uint32_t b_ph = b_phase;
+                if (++b_s == args.b_stages) { b_s = 0; b_phase ^= 1; }
+                mbar_wait(&b_empty[sb], b_ph ^ 1, 42);
                 mbar_arrive_expect_tx(&b_full[sb], kBStageBytes);
                 load_b(smem_b + sb * kBStageBytes, &b_full[sb], r * args.taps_w + sx, chunk, tile_n * BN);
               }
@@ -141,7 +146,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp == 1) {
     // ===== MMA issuer: every tap is a shifted view of the halo brick =====
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
-      uint32_t ia = 0, ib = 0, t = 0;
+      int a_s = 0, b_s = 0;
+      uint32_t a_phase = 0, b_phase = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 45);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
@@ -149,9 +155,11 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
-          for (int cs = 0; cs < args.taps_w; ++cs, ++ia) {
-            const int sa = ia % args.a_stages;
-            mbar_wait(&a_full[sa], (ia / args.a_stages) & 1, 43);
+          for (int cs = 0; cs < args.taps_w; ++cs) {
+            const int sa = a_s;
+            const uint32_t a_ph = a_phase;
+            if (++a_s == args.a_stages) { a_s = 0; a_phase ^= 1; }
+            mbar_wait(&a_full[sa], a_ph, 43);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_a + sa * args.a_slot_bytes);
             for (int dr = 0; dr < args.taps_h; ++dr) {
@@ -163,11 +171,12 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               if (B_RES) {
                 b_addr = smem_u32(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes);
               } else {
-                sb = ib % args.b_stages;
-                mbar_wait(&b_full[sb], (ib / args.b_stages) & 1, 46);
+                sb = b_s;
+                const uint32_t b_ph = b_phase;
+                if (++b_s == args.b_stages) { b_s = 0; b_phase ^= 1; }
+                mbar_wait(&b_full[sb], b_ph, 46);
                 tc_fence_after();
                 b_addr = smem_u32(smem_b + sb * kBStageBytes);
-                ++ib;
               }
               const uint32_t a_view = a_addr + (dr * args.box_n) * 1024;     // whole swizzle atoms: aligned view
 #pragma unroll

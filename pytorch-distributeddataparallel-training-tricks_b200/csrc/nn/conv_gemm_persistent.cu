@@ -123,7 +123,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           }
         }
       }
-      uint32_t it = 0;
+      int ring_s = 0;
+      uint32_t ring_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
         const int tw = tile_m % args.tiles_w;
@@ -131,9 +132,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.box_w, h0 = th * args.box_h, n0 = tn * args.box_n;
         const int col0 = tile_n * BN;
-        for (int step = 0; step < steps_per_tile; ++step, ++it) {
-          const int s = it % kStages;
-          const uint32_t phase = (it / kStages) & 1;
+        for (int step = 0; step < steps_per_tile; ++step) {
+          const int s = ring_s;
+          const uint32_t phase = ring_phase;
+          if (++ring_s == kStages) { ring_s = 0; ring_phase ^= 1; }
           mbar_wait(&empty_bar[s], phase ^ 1, 1);
           const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);
           mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * tx_bytes);
@@ -162,16 +164,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
-      uint32_t it = 0, t = 0;
+      int ring_s = 0;
+      uint32_t ring_phase = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 5);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int step = 0; step < steps_per_tile; ++step, ++it) {
-          const int s = it % kStages;
-          const uint32_t phase = (it / kStages) & 1;
+        for (int step = 0; step < steps_per_tile; ++step) {
+          const int s = ring_s;
+          const uint32_t phase = ring_phase;
+          if (++ring_s == kStages) { ring_s = 0; ring_phase ^= 1; }
           mbar_wait(&full_bar[s], phase, 2);
           tc_fence_after();
           const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);

@@ -338,7 +338,7 @@ __device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, i
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
   extern __shared__ float s_part[];                       // [2][c]
   const int cv = k.c >> 3;
@@ -379,53 +379,77 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
       }
     }
   } else {
-    // (pooled / flattened layouts) walk output positions with incremental 32-bit (pw, ph, img) updates: no
-    // 64-bit divisions in the loop -- they were ~40 % of this kernel's issue slots (profiles/ncu_bnreduce.txt)
+    // (pooled / flattened layouts) walk output positions with incremental 32-bit (pw, ph, img) updates -- no 64-bit
+    // divisions in the loop -- and keep the raw loads of U positions in flight at once: ncu showed this kernel
+    // stalled on the long scoreboard with DRAM only 35 % busy (profiles/ncu_bnreduce.txt).
+    constexpr int U = POOL ? 2 : 1;
     const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
     const unsigned first = blockIdx.x * rows_per_blk + lane_row;
-    int pw = (int)(first % ow), ph = (int)((first / ow) % oh), img = (int)(first / ((unsigned)ow * oh));
-    const int d_pw = (int)(stride32 % ow), d_ph = (int)((stride32 / ow) % oh), d_img = (int)(stride32 / ((unsigned)ow * oh));
-    for (unsigned pix = first; pix < total32; pix += stride32) {
-      float g[8];
-      load_g(k, img, ph, pw, oh, ow, v, g);
-      if (!POOL) {
-        float f[8];
-        unpack8(ldg16(k.y + (size_t)pix * k.c + v * 8), f);
+    const unsigned plane = (unsigned)ow * oh;
+    int pw[U], ph[U], img[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(f[j], sc[j], sh[j]);
-          const float dz = z > 0.f ? g[j] : 0.f;
-          s_dz[j] += dz;
-          s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = first + u * stride32;
+      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
+    }
+    const unsigned step = U * stride32;
+    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
+    for (unsigned pix = first; pix < total32; pix += step) {
+      uint4 yq[U][POOL ? 4 : 1];
+      float g[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        if (POOL) {
+          const __nv_bfloat16* base = k.y + (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
+        } else {
+          yq[u][0] = ldg16(k.y + (size_t)(pix + u * stride32) * k.c + v * 8);
         }
-      } else {
-        const __nv_bfloat16* base = k.y + (((size_t)img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
-        float best[8], besty[8];
+        load_g(k, img[u], ph[u], pw[u], oh, ow, v, g[u]);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }     // z <= 0 everywhere -> no gradient
-        uint4 yq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) yq[q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        if (!POOL) {
           float f[8];
-          unpack8(yq[q], f);
+          unpack8(yq[u][0], f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float z = fmaf(f[j], sc[j], sh[j]);
-            if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
+            const float dz = z > 0.f ? g[u][j] : 0.f;
+            s_dz[j] += dz;
+            s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
+          }
+        } else {
+          float best[8], besty[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }   // z <= 0 everywhere -> no gradient
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(yq[u][q], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = fmaf(f[j], sc[j], sh[j]);
+              if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dz = best[j] > 0.f ? g[u][j] : 0.f;
+            s_dz[j] += dz;
+            s_dzx[j] = fmaf(dz, besty[j], s_dzx[j]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dz = best[j] > 0.f ? g[j] : 0.f;
-          s_dz[j] += dz;
-          s_dzx[j] = fmaf(dz, besty[j], s_dzx[j]);
-        }
       }
-      pw += d_pw; if (pw >= ow) { pw -= ow; ++ph; }
-      ph += d_ph; if (ph >= oh) { ph -= oh; ++img; }
-      img += d_img;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
+        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
+        img[u] += d_img;
+      }
     }
   }
   for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) s_part[i] = 0.f;
@@ -483,7 +507,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                     float* __restrict__ dbias) {
   extern __shared__ float s_db[];                          // [c]
@@ -508,7 +532,7 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
   }
   const long long stride = (long long)gridDim.x * rows_per_blk;
   if (!POOL && !k.flatten) {
-    constexpr int U = 2;
+    constexpr int U = 4;
     for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
       uint4 yv[U], gv[U];
 #pragma unroll
@@ -537,61 +561,86 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       }
     }
   } else {
+    constexpr int U = POOL ? 2 : 1;                        // raw loads of U positions in flight (see bn_bwd_reduce)
     const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
     const unsigned first = blockIdx.x * rows_per_blk + lane_row;
-    int pw = (int)(first % ow), ph = (int)((first / ow) % oh), img = (int)(first / ((unsigned)ow * oh));
-    const int d_pw = (int)(stride32 % ow), d_ph = (int)((stride32 / ow) % oh), d_img = (int)(stride32 / ((unsigned)ow * oh));
-    for (unsigned pix = first; pix < total32; pix += stride32) {
-      float g[8];
-      load_g(k, img, ph, pw, oh, ow, v, g);
-      if (!POOL) {
-        float f[8], o[8];
-        unpack8(ldg16(k.y + (size_t)pix * k.c + v * 8), f);
+    const unsigned plane = (unsigned)ow * oh;
+    int pw[U], ph[U], img[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(f[j], sc[j], sh[j]);
-          const float dz = z > 0.f ? g[j] : 0.f;
-          o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
-          db[j] += o[j];
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = first + u * stride32;
+      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
+    }
+    const unsigned step = U * stride32;
+    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
+    for (unsigned pix = first; pix < total32; pix += step) {
+      uint4 yq[U][POOL ? 4 : 1];
+      float g[U][8];
+      size_t base_off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        if (POOL) {
+          base_off[u] = (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(k.y + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c);
+        } else {
+          base_off[u] = (size_t)(pix + u * stride32) * k.c + v * 8;
+          yq[u][0] = ldg16(k.y + base_off[u]);
         }
-        *reinterpret_cast<uint4*>(dy + (size_t)pix * k.c + v * 8) = pack8(o);
-      } else {
-        const size_t base_off = (((size_t)img * k.h + 2 * ph) * k.w + 2 * pw) * k.c + v * 8;
-        uint4 yq[4];
+        load_g(k, img[u], ph[u], pw[u], oh, ow, v, g[u]);
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) yq[q] = ldg16(k.y + base_off + ((q >> 1) * k.w + (q & 1)) * k.c);
-        // pass A: arg-max of the window (only the winner index is kept; values are re-unpacked in pass B)
-        float best[8];
-        int arg[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-          unpack8(yq[q], f);
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        if (!POOL) {
+          float f[8], o[8];
+          unpack8(yq[u][0], f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float z = fmaf(f[j], sc[j], sh[j]);
-            if (z > best[j]) { best[j] = z; arg[j] = q; }
-          }
-        }
-        // pass B: dy for the four window positions
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8], o[8];
-          unpack8(yq[q], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float dz = arg[j] == q ? g[j] : 0.f;
+            const float dz = z > 0.f ? g[u][j] : 0.f;
             o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
             db[j] += o[j];
           }
-          *reinterpret_cast<uint4*>(dy + base_off + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
+          *reinterpret_cast<uint4*>(dy + base_off[u]) = pack8(o);
+        } else {
+          // pass A: arg-max of the window (only the winner index is kept; values are re-unpacked in pass B)
+          float best[8];
+          int arg[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(yq[u][q], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = fmaf(f[j], sc[j], sh[j]);
+              if (z > best[j]) { best[j] = z; arg[j] = q; }
+            }
+          }
+          // pass B: dy for the four window positions
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8], o[8];
+            unpack8(yq[u][q], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float dz = arg[j] == q ? g[u][j] : 0.f;
+              o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
+              db[j] += o[j];
+            }
+            *reinterpret_cast<uint4*>(dy + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
+          }
         }
       }
-      pw += d_pw; if (pw >= ow) { pw -= ow; ++ph; }
-      ph += d_ph; if (ph >= oh) { ph -= oh; ++img; }
-      img += d_img;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
+        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
+        img[u] += d_img;
+      }
     }
   }
   if (dbias == nullptr) return;

@@ -87,9 +87,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   if (warp == 0) {
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const uint32_t tx_bytes = (kABlocks + kBBlocks) * args.brick_rows * 128;
+      int ring_s = 0;
+      uint32_t ring_phase = 0;
       for (int i = 0; i < num_bricks; ++i) {
-        const int s = i % args.stages;
-        const uint32_t phase = (i / args.stages) & 1;
+        const int s = ring_s;
+        const uint32_t phase = ring_phase;
+        if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&empty_bar[s], phase ^ 1, 11);
         const int brick = brick_begin + i;
         const int bw = brick % args.tiles_w;
@@ -110,9 +113,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   } else if (warp == 1) {
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const int k_steps = args.brick_rows / kUmmaK;
+      int ring_s = 0;
+      uint32_t ring_phase = 0;
       for (int i = 0; i < num_bricks; ++i) {
-        const int s = i % args.stages;
-        const uint32_t phase = (i / args.stages) & 1;
+        const int s = ring_s;
+        const uint32_t phase = ring_phase;
+        if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&full_bar[s], phase, 12);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);

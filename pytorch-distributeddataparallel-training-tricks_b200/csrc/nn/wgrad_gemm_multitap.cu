@@ -103,9 +103,12 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const CUtensorMap* tmx = grp.map == 0 ? &tmap_x0 : &tmap_x1;
       const uint32_t tx_bytes = (kABlocks * args.brick_rows + kBBlocks * grp.halo_rows) * 128;
+      int ring_s = 0;
+      uint32_t ring_phase = 0;
       for (int i = 0; i < num_bricks; ++i) {
-        const int s = i % args.stages;
-        const uint32_t phase = (i / args.stages) & 1;
+        const int s = ring_s;
+        const uint32_t phase = ring_phase;
+        if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&empty_bar[s], phase ^ 1, 31);
         const int brick = brick_begin + i;
         const int bw = brick % args.tiles_w;
@@ -131,9 +134,12 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
       const int gpr = args.box_w / 8;                      // 8-pixel K groups per (h, n) row of the brick
       const int xw = args.box_w + grp.ns - 1;              // halo row width in pixels
       const uint32_t sbo_x = gpr == 1 ? xw * 128 : 1024;
+      int ring_s = 0;
+      uint32_t ring_phase = 0;
       for (int i = 0; i < num_bricks; ++i) {
-        const int s = i % args.stages;
-        const uint32_t phase = (i / args.stages) & 1;
+        const int s = ring_s;
+        const uint32_t phase = ring_phase;
+        if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&full_bar[s], phase, 32);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
