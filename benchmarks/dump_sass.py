@@ -21,7 +21,10 @@ for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.*.o"))):
         ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", f, flags=re.M)
         cnt = collections.Counter(o.split(".")[0] for o in ops)
         rows.append((src, short, len(ops), {k: cnt[k] for k in KEY if cnt[k]}))
-        if any(cnt[k] for k in ("UTCHMMA", "UTMALDG", "LDGMC", "LDTM")):
+        keep = ("conv_gemm_persistent_kernel<256, false, false>", "conv_gemm_halo_kernel<128, false, true>",
+                "wgrad_gemm_kernel<128>", "wgrad_multitap_kernel<64, 256>", "conv_gemm_mxfp8_kernel",
+                "fused_allreduce_kernel<3>", "fused_allreduce_kernel<2>", "fused_lookahead_sgd_kernel")
+        if short in keep:     # full listings only for one representative of every kernel family (the rest: SUMMARY.md)
             fn = re.sub(r"[^A-Za-z0-9_]+", "_", short)[:80]
             with open(os.path.join(OUT, fn + ".sass"), "w") as fh:
                 fh.write(f"// {name}\n// source: csrc/{src}\n" + f)
