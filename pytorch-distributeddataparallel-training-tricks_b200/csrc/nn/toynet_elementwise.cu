@@ -141,20 +141,32 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
     __syncthreads();
     load_image(x, x_is_u8, img, s_img);
     __syncthreads();
-    for (int p = prow; p < kPix0; p += kThreads / 8) {
-      const int oh = p / kOut0, ow = p - oh * kOut0;
-      float g[8];
-      unpack8(ldg16(dy + ((size_t)img * kPix0 + p) * kC0 + cg * 8), g);
-      float in[9];
+    constexpr int kStep = kThreads / 8;                      // 32 pixels per sweep of the block
+    for (int p0 = prow; p0 < kPix0; p0 += 4 * kStep) {
+      uint4 raw[4];                                          // four gradient vectors in flight per thread
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kStep;
+        if (p < kPix0) raw[u] = ldg16(dy + ((size_t)img * kPix0 + p) * kC0 + cg * 8);
+      }
 #pragma unroll
-        for (int q = 0; q < 3; ++q) in[r * 3 + q] = s_img[(oh + r) * kImg + ow + q];
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kStep;
+        if (p >= kPix0) continue;
+        const int oh = p / kOut0, ow = p - oh * kOut0;
+        float g[8];
+        unpack8(raw[u], g);
+        float in[9];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
-        acc[c][9] += g[c];
+          for (int q = 0; q < 3; ++q) in[r * 3 + q] = s_img[(oh + r) * kImg + ow + q];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+          acc[c][9] += g[c];
+        }
       }
     }
   }

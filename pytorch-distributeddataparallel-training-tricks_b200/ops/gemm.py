@@ -197,8 +197,9 @@ def use_multitap(flag: Optional[bool] = None) -> bool:
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
                split_k: Optional[int] = None, accumulate: bool = False, block_n: Optional[int] = None,
-               multitap: Optional[bool] = None):
-    """dW [C_out, kh, kw, C_in] fp32 = sum over pixels dy[p, :]^T x[p + tap, :]."""
+               multitap: Optional[bool] = None, out_is_zero: bool = False):
+    """dW [C_out, kh, kw, C_in] fp32 = sum over pixels dy[p, :]^T x[p + tap, :].  ``out_is_zero``: the caller already
+    cleared ``out`` (e.g. one memset of the whole gradient arena), so split-K partials may be added straight in."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
     c_in = x.shape[3]
@@ -227,7 +228,7 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
             split_k = max(1, min(bricks_of(box), -(-2 * sms // ctas)))
     if out is None:
         out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
-    elif not accumulate and slab is None and split_k > 1:
+    elif not accumulate and slab is None and split_k > 1 and not out_is_zero:
         out.zero_()
     ext.wgrad_gemm(dy, x, out.view(c_out, kh, kw, c_in), [kh, kw], list(box), split_k, accumulate, bn, mt, slab)
     return out
@@ -251,12 +252,13 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = Non
 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
-                 split_k: Optional[int] = None, accumulate: bool = False, multitap: Optional[bool] = None):
+                 split_k: Optional[int] = None, accumulate: bool = False, multitap: Optional[bool] = None,
+                 out_is_zero: bool = False):
     """dw [N, K] fp32 = dy [M, N]^T @ x [M, K]."""
     m, n = dy.shape
     k = x.shape[1]
     res = conv_wgrad(dy.view(1, 1, m, n), x.view(1, 1, m, k), 1, 1,
-                     None if out is None else out.view(n, 1, 1, k), split_k, accumulate, None, multitap)
+                     None if out is None else out.view(n, 1, 1, k), split_k, accumulate, None, multitap, out_is_zero)
     return res.view(n, k)
 
 

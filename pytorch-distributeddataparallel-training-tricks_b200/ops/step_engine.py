@@ -83,7 +83,7 @@ class StepEngine:
         batch = x.shape[0]
         scaler.begin_step()
         arena.grad_arena.zero_()
-        fm.forward_impl(x, True, target=t, metrics=self.metrics)
+        fm.forward_impl(x, True, head=False)      # loss / accuracy come out of the fused head launch in backward
         grads = fm.arena_grads(arena)
         if self.ddp is not None and self.ddp.world_size > 1:
             backend = self.ddp.reducer.backend
@@ -97,12 +97,13 @@ class StepEngine:
                 if pending[b.index] == 0:
                     backend.launch_on(self.comm_stream, main, arena, b, scaler)
 
-            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, on_ready=on_ready)
+            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, on_ready=on_ready,
+                             metrics=self.metrics)
             backend.join(self.comm_stream, main)
             if not backend.fuses_unscale:
                 fo.unscale(scaler)
         else:
-            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor)
+            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, metrics=self.metrics)
             fo.unscale(scaler)
         scaler.update()
         fo.step(self.sgd, self.lookahead)

@@ -90,7 +90,7 @@ class FusedToyNet:
 
     def count_launches(self, batch: int) -> int:
         """Kernels of ours in one training step (forward + backward + unscale + scale update + optimizer)."""
-        fwd = 1 + 1 + 1 + 3 * 3 + 3 + 1          # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio | head
+        fwd = 1 + 1 + 1 + 3 * 3 + 3              # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio (head: in bwd)
         bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
         return fwd + bwd + 3
 
@@ -161,7 +161,7 @@ class FusedToyNet:
             self.ext.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, _EPS, ws.coef[k])
 
     def forward_impl(self, x: torch.Tensor, train: bool, target: Optional[torch.Tensor] = None,
-                     metrics: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     metrics: Optional[torch.Tensor] = None, head: bool = True) -> torch.Tensor:
         ext, P = self.ext, self.params
         if x.dim() == 4:
             if x.shape[1] != 1:
@@ -203,6 +203,8 @@ class FusedToyNet:
                                      False, part, y4.view(1, 1, batch, 512), block_n=64)
         self._bn_coeffs(4, ws, train, 4 * tiles, float(batch))
         ext.bn_relu_pool(ws.y[4], ws.coef[4], ws.a[4], False, False)
+        if not head:       # training step engine: the backward head launch also produces loss / accuracy
+            return ws.logits
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)
         ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, ws.logits, metrics, None, None, None, None, None,
                  float(batch))
@@ -211,7 +213,8 @@ class FusedToyNet:
     # -- backward --------------------------------------------------------------------------------------
     def backward_impl(self, batch: int, grads: List[torch.Tensor], dlogits: Optional[torch.Tensor] = None,
                       target: Optional[torch.Tensor] = None, loss_scale: Optional[torch.Tensor] = None,
-                      on_ready: Optional[Callable[[int], None]] = None) -> None:
+                      on_ready: Optional[Callable[[int], None]] = None,
+                      metrics: Optional[torch.Tensor] = None) -> None:
         """Write d(loss)/d(param) into ``grads`` (zero-initialised by the caller).
 
         Either ``dlogits`` (autograd path) or ``target`` (fused CE with the reference's extra 1/B and the
@@ -220,14 +223,14 @@ class FusedToyNet:
         ext, P, ws = self.ext, self.params, self.workspace(batch)
         ready = on_ready or (lambda i: None)
         x = ws.saved_x
-        ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, None, None, loss_scale, ws.da[4], grads[20],
+        ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, None, metrics, loss_scale, ws.da[4], grads[20],
                  grads[21], dlogits, float(batch))
         ready(21); ready(20)
         # BN1d backward -> dy4
         self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=17)
         ready(19); ready(18); ready(17)
         dy4 = ws.dy[4]
-        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16])
+        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], out_is_zero=True)
         ready(16)
         g = gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
         g = ws.da[3]
@@ -236,7 +239,7 @@ class FusedToyNet:
             h_out = h_in - 2
             self._bn_backward(k, ws, g, grads, pool, k == 3, batch * float(h_out * h_out), dbias_idx=pidx + 1)
             ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
-            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx])
+            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx], out_is_zero=True)
             ready(pidx)
             g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
         self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
