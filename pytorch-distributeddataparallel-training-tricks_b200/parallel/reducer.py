@@ -48,6 +48,16 @@ class ProcessGroupBackend:
             work.wait()
         self._pending.clear()
 
+    # stream-explicit protocol used by the CUDA-graph step engine: the collective is issued synchronously on the
+    # current (capturing) stream -- no overlap, but capturable and correct; this is the NCCL baseline path
+    def launch_on(self, comm_stream, main_stream, arena: FlatArena, bucket: Bucket, scaler=None) -> None:
+        flat = arena.bucket_slice(bucket)
+        flat.div_(self.world)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def join(self, comm_stream, main_stream) -> None:
+        return None
+
 
 class Reducer:
     def __init__(self, arena: FlatArena, backend, find_unused: bool = False):
