@@ -47,6 +47,10 @@ class StepEngine:
         self._static: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._seen_samples = 0
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.ddp is not None else None
+        # weight-gradient GEMMs run on a side stream, off the critical path of backward (DDPT_WGRAD_STREAM=0 disables)
+        import os
+        self.wgrad_stream = (torch.cuda.Stream(device=self.device)
+                             if os.environ.get("DDPT_WGRAD_STREAM", "1") != "0" else None)
         self.kernel_launches_per_step: Dict[Tuple[int, bool], int] = {}
         self.graph_replays = 0
         # optional: copy the metric accumulators to pinned host memory after every step (async, no sync)
@@ -95,15 +99,20 @@ class StepEngine:
                 b = bucket_of[pidx]
                 pending[b.index] -= 1
                 if pending[b.index] == 0:
+                    if self.wgrad_stream is not None:      # the bucket also holds gradients produced on the side stream
+                        ev = torch.cuda.Event()
+                        ev.record(self.wgrad_stream)
+                        self.comm_stream.wait_event(ev)
                     backend.launch_on(self.comm_stream, main, arena, b, scaler)
 
             fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, on_ready=on_ready,
-                             metrics=self.metrics)
+                             metrics=self.metrics, side_stream=self.wgrad_stream)
             backend.join(self.comm_stream, main)
             if not backend.fuses_unscale:
                 fo.unscale(scaler)
         else:
-            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, metrics=self.metrics)
+            fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, metrics=self.metrics,
+                             side_stream=self.wgrad_stream)
             fo.unscale(scaler)
         scaler.update()
         fo.step(self.sgd, self.lookahead)

@@ -214,7 +214,7 @@ class FusedToyNet:
     def backward_impl(self, batch: int, grads: List[torch.Tensor], dlogits: Optional[torch.Tensor] = None,
                       target: Optional[torch.Tensor] = None, loss_scale: Optional[torch.Tensor] = None,
                       on_ready: Optional[Callable[[int], None]] = None,
-                      metrics: Optional[torch.Tensor] = None) -> None:
+                      metrics: Optional[torch.Tensor] = None, side_stream=None) -> None:
         """Write d(loss)/d(param) into ``grads`` (zero-initialised by the caller).
 
         Either ``dlogits`` (autograd path) or ``target`` (fused CE with the reference's extra 1/B and the
@@ -223,6 +223,21 @@ class FusedToyNet:
         ext, P, ws = self.ext, self.params, self.workspace(batch)
         ready = on_ready or (lambda i: None)
         x = ws.saved_x
+        main = torch.cuda.current_stream()
+
+        def off_critical_path(fn):
+            """Weight gradients are leaves of the backward graph: with a side stream they overlap the
+            bandwidth-bound BatchNorm passes and the data-gradient GEMM of the next layer (their CTAs need few
+            registers, so they share SMs with the element-wise kernels)."""
+            if side_stream is None:
+                fn()
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side_stream.wait_event(ev)
+            with torch.cuda.stream(side_stream):
+                fn()
+
         ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, None, metrics, loss_scale, ws.da[4], grads[20],
                  grads[21], dlogits, float(batch))
         ready(21); ready(20)
@@ -230,7 +245,7 @@ class FusedToyNet:
         self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=17)
         ready(19); ready(18); ready(17)
         dy4 = ws.dy[4]
-        gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], out_is_zero=True)
+        off_critical_path(lambda: gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], out_is_zero=True))
         ready(16)
         g = gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
         g = ws.da[3]
@@ -239,12 +254,17 @@ class FusedToyNet:
             h_out = h_in - 2
             self._bn_backward(k, ws, g, grads, pool, k == 3, batch * float(h_out * h_out), dbias_idx=pidx + 1)
             ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
-            gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx], out_is_zero=True)
+            off_critical_path(lambda k=k, pidx=pidx: gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx],
+                                                                     out_is_zero=True))
             ready(pidx)
             g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
         self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
         ready(3); ready(2)
         ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1])
+        if side_stream is not None:                       # join: everything after backward sees all weight gradients
+            ev = torch.cuda.Event()
+            ev.record(side_stream)
+            main.wait_event(ev)
         ready(1); ready(0)
 
     def _bn_backward(self, k: int, ws: _Workspace, g: torch.Tensor, grads, pool: bool, flatten: bool, count: float,
