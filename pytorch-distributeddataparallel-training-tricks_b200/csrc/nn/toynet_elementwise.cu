@@ -258,42 +258,52 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
   shift[c] = beta[c] - rm[c] * sc;
 }
 
-// a = relu(y*scale+shift) [+ 2x2 max-pool]; one thread = one output pixel x 8 channels.
+// a = relu(y*scale+shift) [+ 2x2 max-pool]; a thread owns one 8-channel group and walks output pixels; the raw
+// loads of U pixels are issued before any arithmetic (these passes are latency-, not bandwidth-limited otherwise).
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c) {
+  constexpr int U = POOL ? 2 : 4;
   const int cv = c >> 3;
+  const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
   const int oh = POOL ? h >> 1 : h, ow = POOL ? w >> 1 : w;
-  const long long total = (long long)n * oh * ow * cv;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const int v = (int)(i % cv);
-    const long long pix = i / cv;
-    float sc[8], sh[8];
-    load8f(scale + v * 8, sc);
-    load8f(shift + v * 8, sh);
-    float r[8];
-    if (!POOL) {
-      float f[8];
-      unpack8(ldg16(y + pix * c + v * 8), f);
+  const unsigned total = (unsigned)n * oh * ow;
+  const unsigned stride = gridDim.x * rows_per_blk;
+  float sc[8], sh[8];
+  load8f(scale + v * 8, sc);
+  load8f(shift + v * 8, sh);
+  for (unsigned pix0 = blockIdx.x * rows_per_blk + lane_row; pix0 < total; pix0 += U * stride) {
+    uint4 raw[U][POOL ? 4 : 1];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
-    } else {
-      const int pw = (int)(pix % ow);
-      const int ph = (int)((pix / ow) % oh);
-      const long long img = pix / ((long long)ow * oh);
-      const __nv_bfloat16* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix = pix0 + u * stride;
+      if (pix >= total) continue;
+      if (!POOL) {
+        raw[u][0] = ldg16(y + (size_t)pix * c + v * 8);
+      } else {
+        const unsigned pw = pix % ow, ph = (pix / ow) % oh, img = pix / ((unsigned)ow * oh);
+        const __nv_bfloat16* base = y + (((size_t)img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = 0.f;            // relu floor
+        for (int q = 0; q < 4; ++q) raw[u][q] = ldg16(base + ((q >> 1) * w + (q & 1)) * c);
+      }
+    }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix = pix0 + u * stride;
+      if (pix >= total) continue;
+      float r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = 0.f;              // relu floor
+#pragma unroll
+      for (int q = 0; q < (POOL ? 4 : 1); ++q) {
         float f[8];
-        unpack8(ldg16(base + ((q >> 1) * w + (q & 1)) * c), f);
+        unpack8(raw[u][q], f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) r[k] = fmaxf(r[k], fmaf(f[k], sc[k], sh[k]));
       }
+      *reinterpret_cast<uint4*>(out + (size_t)pix * c + v * 8) = pack8(r);
     }
-    *reinterpret_cast<uint4*>(out + pix * c + v * 8) = pack8(r);
   }
 }
 
@@ -817,8 +827,9 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
     const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
     bn_relu_pool_flatten_kernel<<<n, kThreads, smem, s>>>(y, scale, shift, out, h, w, c);
   } else {
-    const long long total = (long long)n * (pool ? (h / 2) * (w / 2) : h * w) * (c / 8);
-    const int grid = persistent_grid(total, kThreads, 16);
+    const long long pixels = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
+    const int rows_per_blk = kThreads / (c / 8);
+    const int grid = persistent_grid(pixels, rows_per_blk * (pool ? 2 : 4), 8);
     if (pool) bn_relu_pool_kernel<true><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
     else bn_relu_pool_kernel<false><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
   }
