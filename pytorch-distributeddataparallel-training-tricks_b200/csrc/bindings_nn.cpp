@@ -77,14 +77,22 @@ void bn_eval_coeffs(at::Tensor gamma, at::Tensor beta, at::Tensor running_mean, 
                               running_var.data_ptr<float>(), (float)eps, c, co, co + c, cur());
 }
 
-void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bool flatten_chw) {
+void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bool flatten_chw,
+                  c10::optional<at::Tensor> q_out, c10::optional<at::Tensor> q_scale) {
   need(y, at::kBFloat16, "y"); need(coeffs, at::kFloat, "coeffs"); need(out, at::kBFloat16, "out");
   TORCH_CHECK(y.dim() == 4);
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(out.numel() == (pool ? y.numel() / 4 : y.numel()));
   c10::cuda::CUDAGuard g(y.device());
   const float* co = coeffs.data_ptr<float>();
-  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, cur());
+  uint8_t* qd = nullptr; uint8_t* qs = nullptr;
+  if (q_out.has_value()) {
+    TORCH_CHECK(q_scale.has_value());
+    need(*q_out, at::kByte, "q_out"); need(*q_scale, at::kByte, "q_scale");
+    TORCH_CHECK(q_out->numel() == out.numel() && q_scale->numel() == out.numel() / 32);
+    qd = q_out->data_ptr<uint8_t>(); qs = q_scale->data_ptr<uint8_t>();
+  }
+  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, cur());
 }
 
 int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor partials, bool pool, bool flatten_chw) {

@@ -36,8 +36,10 @@ void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* r
                            cudaStream_t s);
 // a = relu(y * scale + shift), optionally followed by 2x2 max-pool; flatten_chw: write the pooled map
 // as [N][C*PH*PW] in (c, h, w) order -- torch's Flatten of an NCHW tensor -- for the first Linear.
+// q_out / q_scale (optional): also emit the activation as MXFP8 (e4m3 [same layout] + UE8M0 per 32 along the last dim)
 void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
-                         int h, int w, int c, int pool, int flatten_chw, cudaStream_t s);
+                         int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
+                         cudaStream_t s);
 
 // ---- BatchNorm backward (two passes) ----------------------------------------------------------------------
 // Pass 1: partials[blk][0][c] = sum dz, partials[blk][1][c] = sum dz * y (finalize converts to sum dz * xhat), dz = grad of the BN output

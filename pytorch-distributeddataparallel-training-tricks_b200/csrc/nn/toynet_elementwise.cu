@@ -12,6 +12,7 @@
 // fixed channel group so per-channel reductions stay in registers until one block-level fold.
 #include "../include/ddpt_toynet.h"
 #include "../include/ddpt_common.cuh"
+#include <cuda_fp8.h>
 #include <stdexcept>
 
 namespace ddpt {
@@ -40,6 +41,24 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// MXFP8 side output of the activation passes ("O1-fp8"): shared UE8M0 exponent of a 32-element block from its amax.
+__device__ __forceinline__ int mx_exponent(float amax) {
+  int e = 127;
+  if (amax > 0.f && is_finite_f32(amax)) {
+    int ex;
+    const float m = frexpf(amax * (1.0f / 448.0f), &ex);
+    e = 127 + ex - (m == 0.5f ? 1 : 0);
+    e = max(1, min(254, e));
+  }
+  return e;
+}
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
+  return (uint32_t)__nv_cvt_float_to_fp8(a, __NV_SATFINITE, __NV_E4M3) |
+         ((uint32_t)__nv_cvt_float_to_fp8(b, __NV_SATFINITE, __NV_E4M3) << 8) |
+         ((uint32_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3) << 16) |
+         ((uint32_t)__nv_cvt_float_to_fp8(d, __NV_SATFINITE, __NV_E4M3) << 24);
 }
 
 int persistent_grid(long long work_items, int per_block, int blocks_per_sm) {
@@ -263,7 +282,8 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c) {
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
+                    uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
   constexpr int U = POOL ? 2 : 4;
   const int cv = c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
@@ -303,6 +323,22 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
         for (int k = 0; k < 8; ++k) r[k] = fmaxf(r[k], fmaf(f[k], sc[k], sh[k]));
       }
       *reinterpret_cast<uint4*>(out + (size_t)pix * c + v * 8) = pack8(r);
+      if (q_out != nullptr) {
+        // block of 32 channels = this lane and its 3 neighbours (same pixel: C/8 is a multiple of 4)
+        float amax = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) amax = fmaxf(amax, r[k]);          // r >= 0 after ReLU
+        const unsigned grp_mask = __activemask();                       // the 4 lanes of a block share `pix`
+        amax = fmaxf(amax, __shfl_xor_sync(grp_mask, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(grp_mask, amax, 2));
+        const int e = mx_exponent(amax);
+        const float inv = exp2f((float)(127 - e));
+        uint2 pk;
+        pk.x = e4m3x4(r[0] * inv, r[1] * inv, r[2] * inv, r[3] * inv);
+        pk.y = e4m3x4(r[4] * inv, r[5] * inv, r[6] * inv, r[7] * inv);
+        *reinterpret_cast<uint2*>(q_out + (size_t)pix * c + v * 8) = pk;
+        if ((v & 3) == 0) q_scale[(size_t)pix * (c >> 5) + (v >> 2)] = (uint8_t)e;
+      }
     }
   }
 }
@@ -310,7 +346,8 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
 // Pooled + flattened in (c, ph, pw) order for the first Linear: one block per image, smem transpose.
 __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c) {
+                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c,
+                            uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
   extern __shared__ __nv_bfloat16 s_t[];                  // [c][ppix + 2] (padded)
   const int oh = h >> 1, ow = w >> 1, ppix = oh * ow, cv = c >> 3, ld = ppix + 2;
   const long long img = blockIdx.x;
@@ -336,6 +373,30 @@ bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __
   __syncthreads();
   __nv_bfloat16* dst = out + img * (long long)c * ppix;
   for (int i = threadIdx.x; i < c * ppix; i += kThreads) dst[i] = s_t[(i / ppix) * ld + (i % ppix)];
+  if (q_out != nullptr) {
+    // MXFP8 copy of the flattened row: blocks of 32 consecutive outputs (the K dimension of the first Linear)
+    const int blocks = c * ppix / 32;
+    for (int b = threadIdx.x; b < blocks; b += kThreads) {
+      float vals[32];
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int i = b * 32 + j;
+        vals[j] = __bfloat162float(s_t[(i / ppix) * ld + (i % ppix)]);
+        amax = fmaxf(amax, vals[j]);
+      }
+      const int e = mx_exponent(amax);
+      const float inv = exp2f((float)(127 - e));
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pk[j] = e4m3x4(vals[4 * j] * inv, vals[4 * j + 1] * inv, vals[4 * j + 2] * inv, vals[4 * j + 3] * inv);
+      uint4* o = reinterpret_cast<uint4*>(q_out + img * (long long)c * ppix + b * 32);
+      o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      q_scale[img * (long long)blocks + b] = (uint8_t)e;
+    }
+  }
 }
 
 // ================================================================================================
@@ -818,20 +879,22 @@ static void check_channels(int c) {
 }
 
 void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
-                         int h, int w, int c, int pool, int flatten_chw, cudaStream_t s) {
+                         int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
+                         cudaStream_t s) {
   check_channels(c);
   if (pool && ((h | w) & 1)) throw std::runtime_error("2x2 max-pool needs even H and W");
   if (flatten_chw) {
     if (!pool) throw std::runtime_error("flatten_chw is only implemented together with the pool");
     const int ppix = (h / 2) * (w / 2);
     const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
-    bn_relu_pool_flatten_kernel<<<n, kThreads, smem, s>>>(y, scale, shift, out, h, w, c);
+    bn_relu_pool_flatten_kernel<<<n, kThreads, smem, s>>>(y, scale, shift, out, h, w, c, q_out, q_scale);
   } else {
     const long long pixels = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
     const int rows_per_blk = kThreads / (c / 8);
     const int grid = persistent_grid(pixels, rows_per_blk * (pool ? 2 : 4), 8);
-    if (pool) bn_relu_pool_kernel<true><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
-    else bn_relu_pool_kernel<false><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c);
+    if (q_out != nullptr && (c % 32 != 0)) throw std::runtime_error("MXFP8 side output needs C % 32 == 0");
+    if (pool) bn_relu_pool_kernel<true><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c, q_out, q_scale);
+    else bn_relu_pool_kernel<false><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c, q_out, q_scale);
   }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
