@@ -301,16 +301,21 @@ def run_reference(args):
         B, K, W = args.batch, args.steps, args.warmup
 
         class SyntheticMNIST(Dataset):                                     # ToTensor-equivalent samples
+            """``n`` samples served from a pool of 8 batches (the index stream still comes from the reference's
+            DistributedSampler; a materialised 1.6 M-image tensor per rank would only measure the host's RAM)."""
+
             def __init__(self, n, seed):
-                xs, ys = zip(*synthetic_batches(max(n // B, 1), B, seed, False))
+                xs, ys = zip(*synthetic_batches(8, B, seed, False))
                 self.x = torch.cat(xs).float().div_(255.0)
                 self.y = torch.cat(ys)
+                self.n = n
 
             def __len__(self):
-                return self.x.shape[0]
+                return self.n
 
             def __getitem__(self, i):
-                return self.x[i], int(self.y[i])
+                j = i % self.x.shape[0]
+                return self.x[j], int(self.y[j])
 
         def loader(n_steps, seed):
             ds = SyntheticMNIST(n_steps * B * world, seed)
