@@ -33,8 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line contract)
+# stdout carries exactly one JSON line: NCCL's banner / debug output (it defaults to stdout) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "MNIST Toy_Net training images/sec (whole job, device-timed, max over ranks)"
 BATCH = 1024

@@ -144,19 +144,23 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t x_addr = a_addr + kABlocks * args.slot_a;
-        if (BN == 64 && grp.ns == 1 && box_taps > 1 && grp.mask == (1 << box_taps) - 1) {
-          // The taps of a filter column are consecutive 64-wide N blocks of ONE wide MMA: tap dr's view of the X
+        if (BN <= 128 && grp.ns == 1 && box_taps > 1 && grp.mask == (1 << box_taps) - 1) {
+          // The taps of a filter column become consecutive 64-wide N blocks of ONE wide MMA: tap dr's view of the X
           // brick starts box_n * xw rows after tap dr-1's, which is exactly the descriptor's leading-dimension
-          // stride.  N = taps * 64 (<= 256) amortises the A-operand fetch and the issue slot over all taps.
-          const uint32_t idesc_wide = make_idesc_bf16(kBlockM, BN * box_taps, true, true);
+          // stride.  N = taps * 64 (<= 256) amortises the A-operand fetch and the issue slot over all taps; a
+          // 128-channel tile is two such MMAs (one per 64-channel block), accumulators laid out [block][tap][64].
+          const uint32_t idesc_wide = make_idesc_bf16(kBlockM, 64 * box_taps, true, true);
           const uint32_t tap_pitch = args.box_n * xw * 128;
           for (int k = 0; k < k_steps; ++k) {
             const int g0 = 2 * k;
             const int row = g0 / gpr, cg = g0 - row * gpr;
             const uint32_t x_off = (row * xw + cg * 8) * 128;
             const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
-            const uint64_t bdesc = make_smem_desc(x_addr + x_off, tap_pitch, sbo_x);
-            mma_bf16_ss(tmem_base, adesc, bdesc, idesc_wide, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int blk = 0; blk < kBBlocks; ++blk) {
+              const uint64_t bdesc = make_smem_desc(x_addr + blk * args.slot_x + x_off, tap_pitch, sbo_x);
+              mma_bf16_ss(tmem_base + blk * 64 * box_taps, adesc, bdesc, idesc_wide, (i | k) != 0 ? 1u : 0u);
+            }
           }
         } else {
           int acc_idx = 0;
@@ -192,12 +196,17 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
       const int dr = t / grp.ns, ds = t - dr * grp.ns;
       const int tap = (grp.r0 + dr) * args.taps_w + grp.s0 + ds;
       float* out_row = dst_base + (static_cast<long long>(m0 + row) * args.num_taps + tap) * args.c_total + c0;
+      const bool merged = BN <= 128 && grp.ns == 1 && box_taps > 1 && grp.mask == (1 << box_taps) - 1;
       const uint32_t tmem_t = tmem_base + acc_idx * BN;
       ++acc_idx;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_t + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        // merged layout: [64-channel block][tap][64]; per-tap layout: [tap][BN]
+        const uint32_t col = merged ? (uint32_t)((c >> 1) * 64 * box_taps + t * 64 + (c & 1) * 32)
+                                    : (uint32_t)((acc_idx - 1) * BN + c * 32);
+        (void)tmem_t;
+        tmem_ld_32x32(tmem_base + col + (static_cast<uint32_t>(quad * 32) << 16), v);
         tmem_ld_wait();
         float* o = out_row + c * 32;
         if (args.slab != nullptr || args.plain) {
