@@ -2,10 +2,17 @@
 # the image already has torch 2.11 + CUDA 12.9, and Apex is replaced by ddpt_b200.amp).
 PYTHON ?= python
 
-.PHONY: build test test-gpu smoke bench bench-ref sass sanitize clean
+.PHONY: build install-all train test test-gpu smoke bench bench-ref sass sanitize clean
+NPROC ?= 1
+PORT ?= 6666
 
 build:            ## compile every CUDA/C++ source for sm_100a into <package>/_ext/_ddpt_C*.so
 	$(PYTHON) -c "import __graft_entry__ as g; g.build()"
+
+install-all: build  ## the reference's entry target (Makefile:7-8); nothing to download here
+
+train:            ## the reference's run line (README.md:28): one process per GPU, run.py -n=DDP_warmup
+	$(PYTHON) -m torch.distributed.run --nnodes=1 --nproc-per-node $(NPROC) --master-addr 127.0.0.1 --master-port $(PORT) run.py -n=DDP_warmup
 
 test:             ## CPU suite (gloo world_size 2, oracle from the reference's shipped logs)
 	$(PYTHON) -m pytest tests -q -m "not gpu"

@@ -21,6 +21,8 @@
 #include "../include/umma.cuh"
 #include "tensor_map.h"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace ddpt {
@@ -57,7 +59,13 @@ struct KernelArgs {
 // B_RES: the whole weight matrix (all taps x channel chunks of the single column block) is loaded into shared
 // memory once per CTA and stays resident; only activation bricks stream through the stage ring.  Halves (fwd) /
 // cuts by a third (dgrad) the L2->SM traffic of layers whose weights fit (Toy_Net conv.3: 144 KiB).
-template <int BN, bool B_MN, bool B_RES>
+//
+// MC = 2: the kernel runs as clusters of two CTAs that work on neighbouring row tiles of the SAME column block in
+// lock step.  Each CTA fetches half of every weight tile and TMA-multicasts it into both shared memories, so a
+// weight tile crosses the L2->SM path once per pair: 48 -> 32 KiB per K block at BN = 256 (the persistent kernels
+// measured L2-fetch bound: tensor pipe 70 % active, profiles/ncu_fwd10.txt).  A stage is released to the producers
+// only when BOTH issuers have finished reading it (tcgen05.commit multicast onto both empty barriers).
+template <int BN, bool B_MN, bool B_RES, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
@@ -65,9 +73,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
 
+  static_assert(MC == 1 || (MC == 2 && !B_RES), "multicast: pairs of CTAs, streamed weights");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  // work units: (group of MC consecutive row tiles) x column block; CTA `rank` of a cluster takes row tile
+  // group * MC + rank.  A row tile past the end (odd tile count) is computed on zero-filled operands and masked.
+  const int rank = MC > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / MC, unit_stride = gridDim.x / MC;
+  const int num_units = ((num_m_tiles + MC - 1) / MC) * num_n_tiles;
+  constexpr uint16_t kMask = (1u << MC) - 1;
   const int total_kb = args.num_taps * args.k_chunks;
   const int kStages = args.stages, kbs = args.kbs;
   const int steps_per_tile = (total_kb + kbs - 1) / kbs;   // pipeline steps (barrier round trips) per tile
@@ -90,7 +104,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -101,7 +115,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (MC > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -125,8 +139,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       }
       int ring_s = 0;
       uint32_t ring_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
         const int tw = tile_m % args.tiles_w;
         const int th = (tile_m / args.tiles_w) % args.tiles_h;
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
@@ -149,6 +163,19 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             uint8_t* b_dst = smem_b + s * b_stage_bytes + j * kBStageBytes;
             if (B_RES) {
               // weights are resident
+            } else if (MC > 1) {
+              // this CTA's half of the weight tile, delivered to both CTAs of the pair
+              if (!B_MN) {
+                tma_load_2d_mc(b_dst + rank * (BN / MC) * 128, &tmap_b, &full_bar[s], kb * kBlockK,
+                               col0 + rank * (BN / MC), kMask);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < BN / 64 / MC; ++jj) {
+                  const int j2 = rank * (BN / 64 / MC) + jj;
+                  tma_load_2d_mc(b_dst + j2 * (kBlockK * 128), &tmap_b, &full_bar[s],
+                                 tap * args.n_total + col0 + j2 * 64, chunk * kBlockK, kMask);
+                }
+              }
             } else if (!B_MN) {
               tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
             } else {
@@ -167,7 +194,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       int ring_s = 0;
       uint32_t ring_phase = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 5);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
         tc_fence_after();
@@ -192,7 +219,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
               mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          mma_commit(&empty_bar[s]);
+          if (MC > 1) mma_commit_mc(&empty_bar[s], kMask); else mma_commit(&empty_bar[s]);
         }
         mma_commit(&tmem_full[acc]);
       }
@@ -212,8 +239,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
     for (int cc = 0; cc < kChunksPerWarp; ++cc) acc_s1[cc] = acc_s2[cc] = 0.f;
     uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++t) {
+      const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
       const int tw = tile_m % args.tiles_w;
       const int th = (tile_m / args.tiles_w) % args.tiles_h;
       const int tn = tile_m / (args.tiles_w * args.tiles_h);
@@ -291,7 +318,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
     if (args.stat_partials != nullptr) {
       // one row group per CTA: [blockIdx.x][quad][2][n_total]; columns of other column blocks are written as 0
-      const int my_tile_n = blockIdx.x % num_n_tiles;
+      const int my_tile_n = unit0 % num_n_tiles;
       float* dst = args.stat_partials + (static_cast<long long>(blockIdx.x) * 4 + quad) * 2 * args.n_total;
       for (int tn2 = 0; tn2 < num_n_tiles; ++tn2) {
 #pragma unroll
@@ -304,14 +331,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
   }
 
-  __syncthreads();
+  // multicast: a CTA may not retire while its peer can still write into its shared memory / arrive on its barriers
+  if (MC > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, bool B_MN, bool B_RES>
+template <int BN, bool B_MN, bool B_RES, int MC = 1>
 int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   constexpr int kBStageBytes = BN * kBlockK * 2;
   const int total_kb_host = p.taps_h * p.taps_w * (p.a_c / kBlockK);
@@ -361,7 +389,7 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   if (!B_MN) {
     const uint64_t b_dims[2] = {(uint64_t)a.num_taps * p.a_c, (uint64_t)p.n_total};
     const uint64_t b_strides[1] = {(uint64_t)p.b_ld * 2};
-    const uint32_t b_box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    const uint32_t b_box[2] = {(uint32_t)kBlockK, (uint32_t)(BN / MC)};
     tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
   } else {
     const uint64_t b_dims[2] = {(uint64_t)a.num_taps * p.n_total, (uint64_t)p.a_c};
@@ -370,29 +398,63 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
     tmap_b = make_tensor_map_bf16(p.b, 2, b_dims, b_strides, b_box);
   }
 
-  auto kernel = conv_gemm_persistent_kernel<BN, B_MN, B_RES>;
+  auto kernel = conv_gemm_persistent_kernel<BN, B_MN, B_RES, MC>;
   static bool configured = false;
-  if (!configured) {
-    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static int max_units = 0;                    // co-resident CTAs (MC = 1) or clusters (MC = 2) at one per SM
   const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
   const int tiles_n_cols = p.n_total / BN;
-  const int total_tiles = tiles_m * tiles_n_cols;
-  int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  grid -= grid % tiles_n_cols;                 // a CTA keeps one column block (statistics accumulate in registers)
-  if (grid < tiles_n_cols) grid = tiles_n_cols;
-  kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
-  DDPT_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  if (MC > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  if (!configured) {
+    DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    max_units = sm_count();
+    if (MC > 1) {
+      // GPCs with an odd number of usable SMs cannot host a last pair: ask the driver how many clusters co-reside
+      cfg.gridDim = dim3(sm_count() / MC * MC);
+      cfg.dynamicSmemBytes = 227 * 1024;
+      DDPT_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_units, kernel, &cfg));
+      cfg.dynamicSmemBytes = smem_bytes;
+      if (max_units < 1) throw std::runtime_error("conv_gemm (persistent): no co-resident cluster");
+      if (std::getenv("DDPT_GEMM_DEBUG") != nullptr)
+        std::fprintf(stderr, "ddpt conv_gemm<%d,%d,mc%d>: %d co-resident clusters on %d SMs\n", BN, (int)B_MN, MC,
+                     max_units, sm_count());
+    }
+    configured = true;
+  }
+  const int total_units = ((tiles_m + MC - 1) / MC) * tiles_n_cols;
+  int units = total_units < max_units ? total_units : max_units;
+  units -= units % tiles_n_cols;               // a CTA keeps one column block (statistics accumulate in registers)
+  if (units < tiles_n_cols) units = tiles_n_cols;
+  const int grid = units * MC;
+  cfg.gridDim = dim3(grid);
+  DDPT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_b, a, tiles_m, tiles_n_cols));
   return p.stat_partials != nullptr ? grid : tiles_m;   // statistic row groups (x4 rows) written
 }
 
 }  // namespace
 
-int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream) {
+int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream, int multicast) {
   // resident weights: one column block, and taps*C*BLOCK_N*2 bytes + a 4-deep activation ring fit in shared memory
   const long long b_bytes = (long long)p.taps_h * p.taps_w * p.a_c * block_n * 2;
   const bool resident = p.n_total == block_n && b_bytes + 4 * kAStageBytes + 2048 <= 227 * 1024 && b_bytes < (1 << 20);
+  if (multicast && !resident && block_n >= 128) {          // CTA pairs share every streamed weight tile
+    if (p.b_mn_major) {
+      if (block_n == 128) return launch_persistent_impl<128, true, false, 2>(p, stream);
+      if (block_n == 256) return launch_persistent_impl<256, true, false, 2>(p, stream);
+    } else {
+      if (block_n == 128) return launch_persistent_impl<128, false, false, 2>(p, stream);
+      if (block_n == 256) return launch_persistent_impl<256, false, false, 2>(p, stream);
+    }
+  }
   if (p.b_mn_major) {
     switch (block_n) {
       case 64: return resident ? launch_persistent_impl<64, true, true>(p, stream) : launch_persistent_impl<64, true, false>(p, stream);

@@ -420,6 +420,56 @@ __device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, i
   }
 }
 
+// ---- packed-bf16 arithmetic for the pooled layers ------------------------------------------------------------
+// The 2x2 window arg-max and the ReLU gate are decided on the raw bf16 conv outputs, two channels per instruction:
+// z = y*sc + sh is monotone in y, so with y' = y ^ sign(sc) (sign bit flipped where sc < 0) the winner is max(y')
+// and z > 0  <=>  y' > thr' with thr' = floor_bf16(-sh/|sc|) (exact for bf16 y; -inf / +inf when sc == 0).
+// ncu on the fp32 formulation: 28.5 M warp instructions, IPC 1.5, DRAM 34 % busy (profiles/ncu_bnreduce.txt) --
+// the pooled passes were issue-bound, not bandwidth-bound; this form needs ~3x fewer instructions and half the
+// registers per window in flight.
+struct PoolConsts { uint32_t sgn[4], thr[4]; };
+
+__device__ __forceinline__ PoolConsts pool_consts(const float (&sc)[8], const float (&sh)[8]) {
+  PoolConsts pc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t sg = 0, th = 0;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const float a = sc[2 * i + hlf], b = sh[2 * i + hlf];
+      const float t = a == 0.f ? (b > 0.f ? -INFINITY : INFINITY) : -b / fabsf(a);
+      const __nv_bfloat16 tb = __float2bfloat16_rd(t);
+      th |= (uint32_t)(*reinterpret_cast<const unsigned short*>(&tb)) << (16 * hlf);
+      sg |= (a < 0.f ? 0x8000u : 0u) << (16 * hlf);
+    }
+    pc.sgn[i] = sg;
+    pc.thr[i] = th;
+  }
+  return pc;
+}
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t x) { return *reinterpret_cast<__nv_bfloat162*>(&x); }
+__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(as_bf162(a), as_bf162(b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+__device__ __forceinline__ uint32_t comp(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// pooled gradient of one output position as four bf16x2 words (NHWC rows, or the flattened [c][oh][ow] layout
+// the first Linear's data gradient is produced in)
+__device__ __forceinline__ uint4 load_g_packed(const BwdCtx& k, int img, int ph, int pw, int oh, int ow, int v) {
+  if (!k.flatten) return ldg16(k.g + (((size_t)img * oh + ph) * ow + pw) * k.c + v * 8);
+  const unsigned short* base = reinterpret_cast<const unsigned short*>(k.g) + (size_t)img * k.c * oh * ow +
+                               (size_t)(v * 8) * oh * ow + ph * ow + pw;
+  const int plane = oh * ow;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (uint32_t)__ldg(base + (2 * i) * plane) | ((uint32_t)__ldg(base + (2 * i + 1) * plane) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
@@ -434,7 +484,60 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_dz[j] = s_dzx[j] = 0.f;
   const long long stride = (long long)gridDim.x * rows_per_blk;
-  if (!POOL && !k.flatten) {
+  if constexpr (POOL) {
+    // output positions are walked with incremental 32-bit (pw, ph, img) updates -- no 64-bit divisions in the loop --
+    // and the raw loads of U windows stay in flight at once
+    constexpr int U = 3;
+    const PoolConsts pc = pool_consts(sc, sh);
+    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
+    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
+    const unsigned plane = (unsigned)ow * oh;
+    int pw[U], ph[U], img[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = first + u * stride32;
+      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
+    }
+    const unsigned step = U * stride32;
+    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
+    for (unsigned pix = first; pix < total32; pix += step) {
+      uint4 yq[U][4], gq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 < total32) {
+          const __nv_bfloat16* base = k.y + (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
+          gq[u] = load_g_packed(k, img[u], ph[u], pw[u], oh, ow, v);
+        } else {
+          gq[u] = make_uint4(0, 0, 0, 0);                  // no gradient -> contributes nothing
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yq[u][q] = make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t sg = pc.sgn[i];
+          const uint32_t best = bmax2(bmax2(comp(yq[u][0], i) ^ sg, comp(yq[u][1], i) ^ sg),
+                                      bmax2(comp(yq[u][2], i) ^ sg, comp(yq[u][3], i) ^ sg));
+          const uint32_t dz = comp(gq[u], i) & __hgt2_mask(as_bf162(best), as_bf162(pc.thr[i]));
+          const uint32_t by = best ^ sg;                   // winner's raw conv output
+          s_dz[2 * i] += bf_lo(dz);
+          s_dz[2 * i + 1] += bf_hi(dz);
+          s_dzx[2 * i] = fmaf(bf_lo(dz), bf_lo(by), s_dzx[2 * i]);
+          s_dzx[2 * i + 1] = fmaf(bf_hi(dz), bf_hi(by), s_dzx[2 * i + 1]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
+        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
+        img[u] += d_img;
+      }
+    }
+  } else if (!k.flatten) {
     constexpr int U = 4;                                  // independent 16-byte loads in flight per thread: 2*U
     for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
       uint4 yv[U], gv[U];
@@ -462,76 +565,19 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
       }
     }
   } else {
-    // (pooled / flattened layouts) walk output positions with incremental 32-bit (pw, ph, img) updates -- no 64-bit
-    // divisions in the loop -- and keep the raw loads of U positions in flight at once: ncu showed this kernel
-    // stalled on the long scoreboard with DRAM only 35 % busy (profiles/ncu_bnreduce.txt).
-    constexpr int U = POOL ? 2 : 1;
-    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
-    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
-    const unsigned plane = (unsigned)ow * oh;
-    int pw[U], ph[U], img[U];
+    // un-pooled activation whose gradient arrives flattened ([c][h][w] per image): small layers only
+    const int plane = oh * ow;
+    for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
+      const int img = (int)(pix / plane), rem = (int)(pix % plane);
+      float f[8], g[8];
+      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
+      load_g(k, img, rem / ow, rem % ow, oh, ow, v, g);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned p = first + u * stride32;
-      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
-    }
-    const unsigned step = U * stride32;
-    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
-    for (unsigned pix = first; pix < total32; pix += step) {
-      uint4 yq[U][POOL ? 4 : 1];
-      float g[U][8];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (pix + u * stride32 >= total32) continue;
-        if (POOL) {
-          const __nv_bfloat16* base = k.y + (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
-        } else {
-          yq[u][0] = ldg16(k.y + (size_t)(pix + u * stride32) * k.c + v * 8);
-        }
-        load_g(k, img[u], ph[u], pw[u], oh, ow, v, g[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (pix + u * stride32 >= total32) continue;
-        if (!POOL) {
-          float f[8];
-          unpack8(yq[u][0], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(f[j], sc[j], sh[j]);
-            const float dz = z > 0.f ? g[u][j] : 0.f;
-            s_dz[j] += dz;
-            s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
-          }
-        } else {
-          float best[8], besty[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { best[j] = 0.f; besty[j] = 0.f; }   // z <= 0 everywhere -> no gradient
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
-            unpack8(yq[u][q], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float z = fmaf(f[j], sc[j], sh[j]);
-              if (z > best[j]) { best[j] = z; besty[j] = f[j]; }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float dz = best[j] > 0.f ? g[u][j] : 0.f;
-            s_dz[j] += dz;
-            s_dzx[j] = fmaf(dz, besty[j], s_dzx[j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
-        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
-        img[u] += d_img;
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float dz = z > 0.f ? g[j] : 0.f;
+        s_dz[j] += dz;
+        s_dzx[j] = fmaf(dz, f[j], s_dzx[j]);
       }
     }
   }
@@ -614,7 +660,75 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
     }
   }
   const long long stride = (long long)gridDim.x * rows_per_blk;
-  if (!POOL && !k.flatten) {
+  if constexpr (POOL) {
+    constexpr int U = 2;                                   // windows (4 + 1 16-byte loads each) in flight
+    const PoolConsts pc = pool_consts(sc, sh);
+    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
+    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
+    const unsigned plane = (unsigned)ow * oh;
+    int pw[U], ph[U], img[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = first + u * stride32;
+      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
+    }
+    const unsigned step = U * stride32;
+    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
+    for (unsigned pix = first; pix < total32; pix += step) {
+      uint4 yq[U][4], gq[U];
+      size_t base_off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        base_off[u] = (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(k.y + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c);
+        gq[u] = load_g_packed(k, img[u], ph[u], pw[u], oh, ow, v);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix + u * stride32 >= total32) continue;
+        // routed gradient of the four window positions, still packed: the first position equal to the window
+        // maximum receives g (if its z > 0), the others 0 -- the same tie rule as max_pool2d's backward
+        uint32_t dz[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t sg = pc.sgn[i];
+          const uint32_t a0 = comp(yq[u][0], i) ^ sg, a1 = comp(yq[u][1], i) ^ sg;
+          const uint32_t a2 = comp(yq[u][2], i) ^ sg, a3 = comp(yq[u][3], i) ^ sg;
+          const uint32_t best = bmax2(bmax2(a0, a1), bmax2(a2, a3));
+          const uint32_t gg = comp(gq[u], i) & __hgt2_mask(as_bf162(best), as_bf162(pc.thr[i]));
+          const uint32_t e0 = __heq2_mask(as_bf162(a0), as_bf162(best));
+          const uint32_t e1 = __heq2_mask(as_bf162(a1), as_bf162(best));
+          const uint32_t e2 = __heq2_mask(as_bf162(a2), as_bf162(best));
+          dz[0][i] = gg & e0;
+          dz[1][i] = gg & e1 & ~e0;
+          dz[2][i] = gg & e2 & ~(e0 | e1);
+          dz[3][i] = gg & ~(e0 | e1 | e2);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t yw = comp(yq[u][q], i);
+            const float lo = fmaf(c1[2 * i], bf_lo(dz[q][i]), fmaf(-k1[2 * i], bf_lo(yw), k0[2 * i]));
+            const float hi = fmaf(c1[2 * i + 1], bf_hi(dz[q][i]), fmaf(-k1[2 * i + 1], bf_hi(yw), k0[2 * i + 1]));
+            db[2 * i] += lo;
+            db[2 * i + 1] += hi;
+            o[i] = pack_bf16x2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(dy + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
+        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
+        img[u] += d_img;
+      }
+    }
+  } else if (!k.flatten) {
     constexpr int U = 4;
     for (long long pix0 = (long long)blockIdx.x * rows_per_blk + lane_row; pix0 < total_pix; pix0 += stride * U) {
       uint4 yv[U], gv[U];
@@ -644,86 +758,20 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       }
     }
   } else {
-    constexpr int U = POOL ? 2 : 1;                        // raw loads of U positions in flight (see bn_bwd_reduce)
-    const unsigned total32 = (unsigned)total_pix, stride32 = (unsigned)stride;
-    const unsigned first = blockIdx.x * rows_per_blk + lane_row;
-    const unsigned plane = (unsigned)ow * oh;
-    int pw[U], ph[U], img[U];
+    const int plane = oh * ow;
+    for (long long pix = (long long)blockIdx.x * rows_per_blk + lane_row; pix < total_pix; pix += stride) {
+      const int img = (int)(pix / plane), rem = (int)(pix % plane);
+      float f[8], g[8], o[8];
+      unpack8(ldg16(k.y + pix * k.c + v * 8), f);
+      load_g(k, img, rem / ow, rem % ow, oh, ow, v, g);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned p = first + u * stride32;
-      pw[u] = (int)(p % ow); ph[u] = (int)((p / ow) % oh); img[u] = (int)(p / plane);
-    }
-    const unsigned step = U * stride32;
-    const int d_pw = (int)(step % ow), d_ph = (int)((step / ow) % oh), d_img = (int)(step / plane);
-    for (unsigned pix = first; pix < total32; pix += step) {
-      uint4 yq[U][POOL ? 4 : 1];
-      float g[U][8];
-      size_t base_off[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (pix + u * stride32 >= total32) continue;
-        if (POOL) {
-          base_off[u] = (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(k.y + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c);
-        } else {
-          base_off[u] = (size_t)(pix + u * stride32) * k.c + v * 8;
-          yq[u][0] = ldg16(k.y + base_off[u]);
-        }
-        load_g(k, img[u], ph[u], pw[u], oh, ow, v, g[u]);
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float dz = z > 0.f ? g[j] : 0.f;
+        o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
+        db[j] += o[j];
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (pix + u * stride32 >= total32) continue;
-        if (!POOL) {
-          float f[8], o[8];
-          unpack8(yq[u][0], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(f[j], sc[j], sh[j]);
-            const float dz = z > 0.f ? g[u][j] : 0.f;
-            o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
-            db[j] += o[j];
-          }
-          *reinterpret_cast<uint4*>(dy + base_off[u]) = pack8(o);
-        } else {
-          // pass A: arg-max of the window (only the winner index is kept; values are re-unpacked in pass B)
-          float best[8];
-          int arg[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { best[j] = 0.f; arg[j] = -1; }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
-            unpack8(yq[u][q], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float z = fmaf(f[j], sc[j], sh[j]);
-              if (z > best[j]) { best[j] = z; arg[j] = q; }
-            }
-          }
-          // pass B: dy for the four window positions
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8], o[8];
-            unpack8(yq[u][q], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float dz = arg[j] == q ? g[u][j] : 0.f;
-              o[j] = fmaf(c1[j], dz, fmaf(-k1[j], f[j], k0[j]));
-              db[j] += o[j];
-            }
-            *reinterpret_cast<uint4*>(dy + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c) = pack8(o);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        pw[u] += d_pw; if (pw[u] >= ow) { pw[u] -= ow; ++ph[u]; }
-        ph[u] += d_ph; if (ph[u] >= oh) { ph[u] -= oh; ++img[u]; }
-        img[u] += d_img;
-      }
+      *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
     }
   }
   if (dbias == nullptr) return;

@@ -72,9 +72,18 @@ def pick_box_halo(out_n: int, out_h: int, out_w: int, kh: int = 3, kw: int = 3,
     return best, best_key[0]
 
 
+def use_multicast(flag: Optional[bool] = None) -> bool:
+    """2-CTA clusters with TMA-multicast weight tiles for the persistent kernel (128/256-wide tiles, streamed
+    weights).  DDPT_GEMM_MULTICAST=0/1 overrides."""
+    if flag is not None:
+        return flag
+    return os.environ.get("DDPT_GEMM_MULTICAST", "0") == "1"
+
+
 def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: int, kw: int, c_k: int, n_total: int,
-               bn: int):
-    """(mode, box): 0 per-tile, 1 persistent, 2 persistent + halo reuse (see csrc/nn/conv_gemm_halo.cu)."""
+               bn: int, multicast: Optional[bool] = None):
+    """(mode, box): 0 per-tile, 1 persistent, 2 persistent + halo reuse (see csrc/nn/conv_gemm_halo.cu),
+    3 persistent in 2-CTA clusters with multicast weight tiles."""
     if not use_persistent(persistent):
         return 0, pick_box(*out_nhw)
     env = os.environ.get("DDPT_GEMM_HALO", "1")
@@ -87,12 +96,12 @@ def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: in
         # resident weights leave (227 KiB - weights) / 3 per activation slot (three bricks in flight)
         max_rows = ((227 * 1024 - 2048 - b_bytes) // 3) // 128 if resident else 1 << 30
         box, eff = pick_box_halo(*out_nhw, kh, kw, max_rows)
-        # measured (profiles/kernel_probe_*.json): the halo variant wins only when the weights are resident AND
-        # the 8-pixel bricks tile the output exactly (Toy_Net conv.3 forward: 866 vs 758 TFLOP/s); row padding or
-        # streamed weights make it lose to the plain persistent kernel, so those cases stay on mode 1
-        if box is not None and (halo or (resident and eff >= 0.95)):
+        # measured (profiles/kernel_probe_b1024.json): the halo variant wins when the weights are resident (Toy_Net
+        # conv.3 forward 81 vs 128 us with exact 8-pixel tiling; conv.3 data gradient 177 vs 218 us even with 19 %
+        # padded rows); streamed weights make it lose to the plain persistent kernel, so those cases stay on mode 1
+        if box is not None and (halo or (resident and eff >= 0.8)):
             return 2, box
-    return 1, pick_box(*out_nhw)
+    return (3 if bn >= 128 and use_multicast(multicast) else 1), pick_box(*out_nhw)
 
 
 def _block_n(n_total: int, prefer: Optional[int]) -> int:
@@ -118,7 +127,7 @@ def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Opt
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-             persistent: Optional[bool] = None, halo: Optional[bool] = None):
+             persistent: Optional[bool] = None, halo: Optional[bool] = None, multicast: Optional[bool] = None):
     """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
     ext = require_native()
     n, h, w, c = x.shape
@@ -127,14 +136,15 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
     if out is None:
         out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
     bn = _block_n(c_out, block_n)
-    mode, box = (0, pick_box(n, ho, wo)) if split_k > 1 else _gemm_mode(persistent, halo, (n, ho, wo), kh, kw, c, c_out, bn)
+    mode, box = (0, pick_box(n, ho, wo)) if split_k > 1 else _gemm_mode(persistent, halo, (n, ho, wo), kh, kw, c, c_out, bn, multicast)
     tiles = ext.conv_gemm(x, w_km, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], 1, [0, 0], False,
                           bias, relu, stat_partials, split_k, bn, mode)
     return out, tiles
 
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
-               block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None,
+               multicast: Optional[bool] = None):
     """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
@@ -143,7 +153,7 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
     if out is None:
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
     bn = _block_n(c_in, block_n)
-    mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn)
+    mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, multicast)
     ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
                   None, False, None, 1, bn, mode)
     return out
@@ -187,8 +197,8 @@ def _slab(device, numel: int) -> torch.Tensor:
 
 def use_multitap(flag: Optional[bool] = None) -> bool:
     """Halo-reuse weight-gradient kernel (csrc/nn/wgrad_gemm_multitap.cu).  DDPT_WGRAD_MULTITAP=0/1 forces it off /
-    on; by default (None) the caller enables it only where it measured faster: C_in == 64, where a filter column's
-    three taps merge into one N = 192 MMA (2.06 vs 2.13 ms/step end to end)."""
+    on; by default (None) the caller enables it only where it measured faster (see conv_wgrad): a filter column's
+    taps merge into one wide-N MMA per k-step (N = 192 for 64-wide tiles, 2 x N = 192 for 128-wide tiles)."""
     if flag is not None:
         return flag
     env = os.environ.get("DDPT_WGRAD_MULTITAP")
@@ -208,7 +218,10 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
     bn = _block_n(c_in, block_n)
     mt = use_multitap(multitap)
     if mt is None:
-        mt = bn == 64 and kh * kw > 1
+        # measured (profiles/kernel_probe_b1024.json): the merged wide-N kernel wins for 64-wide tiles (conv.3: 99 vs
+        # 169 us) and for 128-wide tiles when the un-split grid already has >= 16 CTAs (conv.10: 124 vs 176 us); with
+        # fewer CTAs the deeper split-K slab reduction eats the gain (conv.7: 95 vs 87 us)
+        mt = kh * kw > 1 and (bn == 64 or (bn == 128 and (c_out // 128) * kw * (c_in // bn) >= 16))
     bricks_of = lambda b: -(-wo // b[2]) * -(-ho // b[1]) * -(-n // b[0])
     sms = torch.cuda.get_device_properties(dy.device).multi_processor_count
     slab = None
@@ -236,19 +249,19 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
                stat_partials: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-               block_n: Optional[int] = None, persistent: Optional[bool] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None, multicast: Optional[bool] = None):
     """y [M, N] = x [M, K] @ w [N, K]^T (+ bias)."""
     m, k = x.shape
     y, tiles = conv_fwd(x.view(1, 1, m, k), w, 1, 1, bias, relu, stat_partials, None, block_n, out_dtype, split_k,
-                        persistent)
+                        persistent, None, multicast)
     return y.view(m, w.shape[0]), tiles
 
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None,
-                 persistent: Optional[bool] = None):
+                 persistent: Optional[bool] = None, multicast: Optional[bool] = None):
     """dx [M, K] = dy [M, N] @ w [N, K]."""
     m, n = dy.shape
-    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n, persistent).view(m, w.shape[1])
+    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n, persistent, None, multicast).view(m, w.shape[1])
 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
