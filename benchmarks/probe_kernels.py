@@ -50,14 +50,14 @@ def main():
             flops = 2.0 * B * (h - 2) * (w - 2) * co * ci * 9
             for bn in (64, 128, 256):
                 for pers, halo, mc, tag in ((False, False, False, ""), (True, False, False, ".persist"),
-                                            (True, True, False, ".halo"), (True, False, True, ".mcast")):
+                                            (True, True, False, ".halo"), (True, False, True, ".pair")):
                     if mc and bn < 128:
                         continue
                     if co % bn == 0:
-                        t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn, persistent=pers, halo=halo, multicast=mc), flush=flush)
+                        t = timeit(lambda: gemm.conv_fwd(x, wk, 3, 3, block_n=bn, persistent=pers, halo=halo, pair=mc), flush=flush)
                         rows.append(dict(op=f"{name}.fwd{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                     if ci % bn == 0:
-                        t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn, persistent=pers, halo=halo, multicast=mc), flush=flush)
+                        t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, block_n=bn, persistent=pers, halo=halo, pair=mc), flush=flush)
                         rows.append(dict(op=f"{name}.dgrad{tag}", block_n=bn, ms=t, tflops=flops / t / 1e9))
                 if ci % bn == 0:
                     dw = torch.zeros(co, 3, 3, ci, device="cuda")
@@ -80,8 +80,8 @@ def main():
             rows.append(dict(op="dense.1.fwd", block_n=bn, split_k=sk, ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: gemm.linear_dgrad(dy, w1), flush=flush)
         rows.append(dict(op="dense.1.dgrad", ms=t, tflops=fl / t / 1e9))
-        t = timeit(lambda: gemm.linear_dgrad(dy, w1, multicast=True), flush=flush)
-        rows.append(dict(op="dense.1.dgrad.mcast", ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: gemm.linear_dgrad(dy, w1, pair=True), flush=flush)
+        rows.append(dict(op="dense.1.dgrad.pair", ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: gemm.linear_wgrad(dy, x), flush=flush)
         rows.append(dict(op="dense.1.wgrad", ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: x @ w1.t(), flush=flush)

@@ -168,7 +168,7 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
   }
   // mode: 0 = one CTA per tile (split-K capable), 1 = persistent, 2 = persistent + halo reuse
   if (mode == 2 && split_k <= 1) return ddpt::launch_conv_gemm_halo(p, (int)block_n, current_stream());
-  // mode 3: persistent kernel as 2-CTA clusters with TMA-multicast weight tiles
+  // mode 3: persistent kernel as CTA pairs (tcgen05 cta_group::2, 256-row tiles)
   if (mode >= 1 && split_k <= 1) return ddpt::launch_conv_gemm_persistent(p, (int)block_n, current_stream(), mode == 3);
   return ddpt::launch_conv_gemm(p, (int)block_n, current_stream());
 }

@@ -44,7 +44,7 @@ struct ConvGemmProblem {
 int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
 // Persistent variant (one CTA per SM, double-buffered TMEM accumulator); no split-K.  With stat_partials the
 // statistics are accumulated per CTA and the return value is the number of row groups written (= grid size).
-int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream, int multicast = 0);
+int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream, int cta_pair = 0);
 // Halo-reuse variant: the activation brick (+halo) is loaded once per channel chunk and every filter tap is a
 // shifted descriptor view; requires box_w == 8 and box_h * box_n <= 16.  Same return convention as persistent.
 int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t stream);

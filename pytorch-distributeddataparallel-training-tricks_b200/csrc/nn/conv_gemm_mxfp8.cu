@@ -123,14 +123,14 @@ conv_gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int th = (tile_m / args.tiles_w) % args.tiles_h;
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.box_w, h0 = th * args.box_h, n0 = tn * args.box_n;
+        int chunk = 0, sx = 0, r = 0;          // (filter tap, channel chunk) of the K block: counters, no divisions
         for (int kb = 0; kb < total_kb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1, 61);
-          const int tap = kb / args.k_chunks, chunk = kb - tap * args.k_chunks;
-          const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(smem_a + s * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockKBytes, w0 + sx, h0 + r, n0);
           tma_load_2d(smem_b + s * kBStageBytes, &tmap_b, &full_bar[s], kb * kBlockKBytes, tile_n * kBlockN);
+          if (++chunk == args.k_chunks) { chunk = 0; if (++sx == args.taps_w) { sx = 0; ++r; } }
         }
       }
     }
@@ -190,10 +190,11 @@ conv_gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         b_rows[c] = args.b_scale + static_cast<long long>(tile_n * kBlockN + c * 32 + lane) * b_words_per_row;
+      int chunk_c = 0, sx_c = 0, r_c = 0;
       for (int kb = 0; kb < total_kb; ++kb, ++it) {
         const int s = it % kStages;
-        const int tap = kb / args.k_chunks, chunk = kb - tap * args.k_chunks;
-        const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
+        const int chunk = chunk_c, sx = sx_c, r = r_c;
+        if (++chunk_c == args.k_chunks) { chunk_c = 0; if (++sx_c == args.taps_w) { sx_c = 0; ++r_c; } }
         uint32_t wa[4], wb[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

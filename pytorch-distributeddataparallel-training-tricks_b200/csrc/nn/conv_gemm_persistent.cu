@@ -60,20 +60,24 @@ struct KernelArgs {
 // memory once per CTA and stays resident; only activation bricks stream through the stage ring.  Halves (fwd) /
 // cuts by a third (dgrad) the L2->SM traffic of layers whose weights fit (Toy_Net conv.3: 144 KiB).
 //
-// MC = 2: the kernel runs as clusters of two CTAs that work on neighbouring row tiles of the SAME column block in
-// lock step.  Each CTA fetches half of every weight tile and TMA-multicasts it into both shared memories, so a
-// weight tile crosses the L2->SM path once per pair: 48 -> 32 KiB per K block at BN = 256 (the persistent kernels
-// measured L2-fetch bound: tensor pipe 70 % active, profiles/ncu_fwd10.txt).  A stage is released to the producers
-// only when BOTH issuers have finished reading it (tcgen05.commit multicast onto both empty barriers).
+// MC = 2 (CTA pair, tcgen05 cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- compute a 256 x BN tile
+// with ONE paired MMA stream issued by the leader.  Each CTA stages its own 128 activation rows and HALF of the
+// weight tile, so per K block a CTA's shared memory takes 32 KiB of TMA writes and 8 KiB of operand reads per MMA
+// instead of 48 / 12 KiB at BN = 256.  Why: the single-CTA kernel plateaued at 70 % tensor-pipe activity with TMA
+// writes (94 B/clk) + operand reads (96 B/clk) ~ 1.4x the 128 B/clk shared-memory port; TMA multicast of the weight
+// tile alone (same bytes written, fewer L2 reads) measured +-0 % (profiles/README.md), i.e. the port, not L2, binds.
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (cta_group::2 loads, peer bit cleared)
+//   * tcgen05.commit.cta_group::2 multicasts stage release / accumulator-ready onto both CTAs' barriers
+//   * both CTAs' epilogue warps arrive on the leader's tmem_empty barrier (remote mbarrier arrive)
 template <int BN, bool B_MN, bool B_RES, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
-  constexpr int kBStageBytes = BN * kBlockK * 2;            // one K block of B
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+  constexpr int kBStageBytes = (BN / MC) * kBlockK * 2;     // one K block of B (this CTA's share of the columns)
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM * MC, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
 
-  static_assert(MC == 1 || (MC == 2 && !B_RES), "multicast: pairs of CTAs, streamed weights");
+  static_assert(MC == 1 || (MC == 2 && !B_RES && BN >= 128), "CTA pair: streamed weights, >= 64 columns per CTA");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // work units: (group of MC consecutive row tiles) x column block; CTA `rank` of a cluster takes row tile
@@ -104,18 +108,20 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MC);
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpilogueWarps);
+      mbar_init(&tmem_empty[s], kEpilogueWarps * MC);      // pair: the leader collects both CTAs' epilogues
     }
     mbar_init(b_ready, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (MC > 1) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  if (MC > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything is multicast
+  if (MC > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -144,45 +150,44 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int tw = tile_m % args.tiles_w;
         const int th = (tile_m / args.tiles_w) % args.tiles_h;
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
-        const int w0 = tw * args.box_w, h0 = th * args.box_h, n0 = tn * args.box_n;
-        const int col0 = tile_n * BN;
+        // A-box origin of tap (0, 0) and the weight column of this CTA; the (tap, channel chunk) of each K block is
+        // advanced with counters.  ncu on the first version (profiles/ncu_fwd10_pair_v1.txt): the elected producer
+        // lane spent ~85 % of its samples in two runtime integer divisions per K block (I2F / MUFU.RCP chains on one
+        // in-order thread, ~600 clk) while its empty-slot wait never spun -- the producer, not L2 or shared memory,
+        // capped every variant of this kernel at 70 % tensor-pipe activity.
+        const int wb = tw * args.box_w + args.a_w_off, hb = th * args.box_h + args.a_h_off, n0 = tn * args.box_n;
+        const int col0 = tile_n * BN + (MC > 1 ? rank * (BN / MC) : 0);
+        int kb = 0, chunk = 0, sx = 0, dh = 0, tap_col = col0;   // tap_col: B_MN column of this tap = tap * n_total + col0
         for (int step = 0; step < steps_per_tile; ++step) {
           const int s = ring_s;
           const uint32_t phase = ring_phase;
           if (++ring_s == kStages) { ring_s = 0; ring_phase ^= 1; }
           mbar_wait(&empty_bar[s], phase ^ 1, 1);
-          const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);
-          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * tx_bytes);
-          for (int j = 0; j < nkb; ++j) {
-            const int kb = kb0 + j;
-            const int tap = kb / args.k_chunks;
-            const int chunk = kb - tap * args.k_chunks;
-            const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
-            tma_load_4d(smem_a + s * a_stage_bytes + j * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
-                        w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
-            uint8_t* b_dst = smem_b + s * b_stage_bytes + j * kBStageBytes;
+          const int nkb = min(kbs, total_kb - kb);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * MC * tx_bytes);
+          uint8_t* a_dst = smem_a + s * a_stage_bytes;
+          uint8_t* b_dst = smem_b + s * b_stage_bytes;
+          for (int j = 0; j < nkb; ++j, a_dst += kAStageBytes, b_dst += kBStageBytes) {
+            if (MC > 1) tma_load_4d_pair(a_dst, &tmap_a, &full_bar[s], chunk * kBlockK, wb + sx, hb + dh, n0);
+            else tma_load_4d(a_dst, &tmap_a, &full_bar[s], chunk * kBlockK, wb + sx, hb + dh, n0);
             if (B_RES) {
               // weights are resident
-            } else if (MC > 1) {
-              // this CTA's half of the weight tile, delivered to both CTAs of the pair
-              if (!B_MN) {
-                tma_load_2d_mc(b_dst + rank * (BN / MC) * 128, &tmap_b, &full_bar[s], kb * kBlockK,
-                               col0 + rank * (BN / MC), kMask);
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < BN / 64 / MC; ++jj) {
-                  const int j2 = rank * (BN / 64 / MC) + jj;
-                  tma_load_2d_mc(b_dst + j2 * (kBlockK * 128), &tmap_b, &full_bar[s],
-                                 tap * args.n_total + col0 + j2 * 64, chunk * kBlockK, kMask);
-                }
-              }
             } else if (!B_MN) {
-              tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
+              if (MC > 1) tma_load_2d_pair(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
+              else tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
             } else {
 #pragma unroll
-              for (int jj = 0; jj < BN / 64; ++jj)
-                tma_load_2d(b_dst + jj * (kBlockK * 128), &tmap_b, &full_bar[s],
-                            tap * args.n_total + col0 + jj * 64, chunk * kBlockK);
+              for (int jj = 0; jj < BN / 64 / MC; ++jj) {
+                if (MC > 1) tma_load_2d_pair(b_dst + jj * (kBlockK * 128), &tmap_b, &full_bar[s], tap_col + jj * 64, chunk * kBlockK);
+                else tma_load_2d(b_dst + jj * (kBlockK * 128), &tmap_b, &full_bar[s], tap_col + jj * 64, chunk * kBlockK);
+              }
+            }
+            ++kb;
+            if (++chunk == args.k_chunks) {                 // next filter tap: one column right, or next row
+              chunk = 0;
+              tap_col += args.n_total;
+              sx += args.tap_sign;
+              if (sx == args.tap_sign * args.taps_w) { sx = 0; dh += args.tap_sign; }
             }
           }
         }
@@ -190,7 +195,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
+    if ((MC == 1 || rank == 0) && elect_one()) {   // one elected lane (of the leader CTA): uniform-register operands
       int ring_s = 0;
       uint32_t ring_phase = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 5);
@@ -216,12 +221,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
               const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
               const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
                                           : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
-              mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              if (MC > 1) mma_bf16_ss_pair(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              else mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          if (MC > 1) mma_commit_mc(&empty_bar[s], kMask); else mma_commit(&empty_bar[s]);
+          if (MC > 1) mma_commit_pair(&empty_bar[s], kMask); else mma_commit(&empty_bar[s]);
         }
-        mma_commit(&tmem_full[acc]);
+        if (MC > 1) mma_commit_pair(&tmem_full[acc], kMask); else mma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -314,7 +320,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (MC > 1) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (args.stat_partials != nullptr) {
       // one row group per CTA: [blockIdx.x][quad][2][n_total]; columns of other column blocks are written as 0
@@ -331,17 +339,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
   }
 
-  // multicast: a CTA may not retire while its peer can still write into its shared memory / arrive on its barriers
+  // pair: a CTA may not retire (or free TMEM) while the leader's MMAs can still read its shared memory / write its
+  // accumulator, or while the peer can still arrive on its barriers
   if (MC > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (MC > 1) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
 template <int BN, bool B_MN, bool B_RES, int MC = 1>
 int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
-  constexpr int kBStageBytes = BN * kBlockK * 2;
+  constexpr int kBStageBytes = (BN / MC) * kBlockK * 2;
   const int total_kb_host = p.taps_h * p.taps_w * (p.a_c / kBlockK);
   // K blocks per pipeline stage: a barrier round trip (try_wait + fence + commit, ~300 cycles) should be covered by
   // >= ~512 tensor cycles of MMAs; one K block is 4 x (BN/4) cycles.  ncu on conv.3 dgrad (N = 64, one K block per
@@ -442,11 +451,11 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream, int multicast) {
+int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStream_t stream, int cta_pair) {
   // resident weights: one column block, and taps*C*BLOCK_N*2 bytes + a 4-deep activation ring fit in shared memory
   const long long b_bytes = (long long)p.taps_h * p.taps_w * p.a_c * block_n * 2;
   const bool resident = p.n_total == block_n && b_bytes + 4 * kAStageBytes + 2048 <= 227 * 1024 && b_bytes < (1 << 20);
-  if (multicast && !resident && block_n >= 128) {          // CTA pairs share every streamed weight tile
+  if (cta_pair && !resident && block_n >= 128) {          // CTA pairs (cta_group::2): 256-row tiles, weights split
     if (p.b_mn_major) {
       if (block_n == 128) return launch_persistent_impl<128, true, false, 2>(p, stream);
       if (block_n == 256) return launch_persistent_impl<256, true, false, 2>(p, stream);

@@ -89,16 +89,18 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       const uint32_t tx_bytes = (kABlocks + kBBlocks) * args.brick_rows * 128;
       int ring_s = 0;
       uint32_t ring_phase = 0;
+      // brick coordinates advance with counters: runtime divisions on this one in-order thread cost more than the
+      // MMAs of a brick (the producer lane was the bottleneck of the GEMM kernels, profiles/ncu_fwd10_pair_v1.txt)
+      int bw = brick_begin % args.tiles_w;
+      int bh = (brick_begin / args.tiles_w) % args.tiles_h;
+      int bn = brick_begin / (args.tiles_w * args.tiles_h);
       for (int i = 0; i < num_bricks; ++i) {
         const int s = ring_s;
         const uint32_t phase = ring_phase;
         if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&empty_bar[s], phase ^ 1, 11);
-        const int brick = brick_begin + i;
-        const int bw = brick % args.tiles_w;
-        const int bh = (brick / args.tiles_w) % args.tiles_h;
-        const int bn = brick / (args.tiles_w * args.tiles_h);
         const int w0 = bw * args.box_w, h0 = bh * args.box_h, n0 = bn * args.box_n;
+        if (++bw == args.tiles_w) { bw = 0; if (++bh == args.tiles_h) { bh = 0; ++bn; } }
         uint8_t* stage = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
 #pragma unroll

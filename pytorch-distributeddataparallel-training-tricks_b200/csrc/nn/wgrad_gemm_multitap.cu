@@ -105,16 +105,17 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
       const uint32_t tx_bytes = (kABlocks * args.brick_rows + kBBlocks * grp.halo_rows) * 128;
       int ring_s = 0;
       uint32_t ring_phase = 0;
+      // brick coordinates advance with counters (no runtime divisions on the single producer lane)
+      int bw = brick_begin % args.tiles_w;
+      int bh = (brick_begin / args.tiles_w) % args.tiles_h;
+      int bn = brick_begin / (args.tiles_w * args.tiles_h);
       for (int i = 0; i < num_bricks; ++i) {
         const int s = ring_s;
         const uint32_t phase = ring_phase;
         if (++ring_s == args.stages) { ring_s = 0; ring_phase ^= 1; }
         mbar_wait(&empty_bar[s], phase ^ 1, 31);
-        const int brick = brick_begin + i;
-        const int bw = brick % args.tiles_w;
-        const int bh = (brick / args.tiles_w) % args.tiles_h;
-        const int bn = brick / (args.tiles_w * args.tiles_h);
         const int w0 = bw * args.box_w, h0 = bh * args.box_h, n0 = bn * args.box_n;
+        if (++bw == args.tiles_w) { bw = 0; if (++bh == args.tiles_h) { bh = 0; ++bn; } }
         uint8_t* stage = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
         // tensor maps are declared (C, W, N, H): the brick's pixel order in shared memory is w, then n, then h
@@ -151,10 +152,13 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
           // 128-channel tile is two such MMAs (one per 64-channel block), accumulators laid out [block][tap][64].
           const uint32_t idesc_wide = make_idesc_bf16(kBlockM, 64 * box_taps, true, true);
           const uint32_t tap_pitch = args.box_n * xw * 128;
+          // K step k covers the 8-pixel groups 2k, 2k+1 of the brick: (row, column group) advance with counters --
+          // a runtime division per MMA on the issuing lane costs more than the MMA itself
+          int row = 0, cg = 0;
           for (int k = 0; k < k_steps; ++k) {
-            const int g0 = 2 * k;
-            const int row = g0 / gpr, cg = g0 - row * gpr;
             const uint32_t x_off = (row * xw + cg * 8) * 128;
+            cg += 2;
+            while (cg >= gpr) { cg -= gpr; ++row; }
             const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
 #pragma unroll
             for (int blk = 0; blk < kBBlocks; ++blk) {
@@ -163,16 +167,18 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
             }
           }
         } else {
-          int acc_idx = 0;
+          int acc_idx = 0, dr = 0, ds = 0;
           for (int t = 0; t < box_taps; ++t) {
+            const int dr_t = dr, ds_t = ds;                   // tap t = (dr, ds) of the group, row-major
+            if (++ds == grp.ns) { ds = 0; ++dr; }
             if (!((grp.mask >> t) & 1)) continue;
-            const int dr = t / grp.ns, ds = t - dr * grp.ns;
             const uint32_t tmem_d = tmem_base + acc_idx * BN;
             ++acc_idx;
+            int row = 0, cg = 0;                              // (h, n) row of the brick, 8-pixel column group
             for (int k = 0; k < k_steps; ++k) {
-              const int g0 = 2 * k;                           // first of the two 8-pixel K groups of this step
-              const int row = g0 / gpr, cg = g0 - row * gpr;  // (h, n) row of the brick, 8-pixel column group
-              const uint32_t x_off = ((row + dr * args.box_n) * xw + cg * 8 + ds) * 128;
+              const uint32_t x_off = ((row + dr_t * args.box_n) * xw + cg * 8 + ds_t) * 128;
+              cg += 2;
+              while (cg >= gpr) { cg -= gpr; ++row; }
               const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
               const uint64_t bdesc = make_smem_desc(x_addr + x_off, args.slot_x, sbo_x);
               mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);

@@ -72,18 +72,20 @@ def pick_box_halo(out_n: int, out_h: int, out_w: int, kh: int = 3, kw: int = 3,
     return best, best_key[0]
 
 
-def use_multicast(flag: Optional[bool] = None) -> bool:
-    """2-CTA clusters with TMA-multicast weight tiles for the persistent kernel (128/256-wide tiles, streamed
-    weights).  DDPT_GEMM_MULTICAST=0/1 overrides."""
+def use_cta_pair(flag: Optional[bool] = None) -> bool:
+    """Run the persistent kernel as CTA pairs (tcgen05 ``cta_group::2``: two SMs share one 256-row MMA, each stages
+    half of the weight tile); 128/256-wide tiles with streamed weights only.  DDPT_GEMM_PAIR=0/1 overrides."""
     if flag is not None:
         return flag
-    return os.environ.get("DDPT_GEMM_MULTICAST", "0") == "1"
+    # measured (profiles/kernel_probe_b1024.json): conv.10 forward 98 vs 111 us, conv.10 dgrad 156 vs 164 us,
+    # conv.7 forward 51 vs 60 us, conv.7 dgrad 72 vs 86 us; never slower where it applies -> on by default
+    return os.environ.get("DDPT_GEMM_PAIR", "1") == "1"
 
 
 def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: int, kw: int, c_k: int, n_total: int,
-               bn: int, multicast: Optional[bool] = None):
+               bn: int, pair: Optional[bool] = None):
     """(mode, box): 0 per-tile, 1 persistent, 2 persistent + halo reuse (see csrc/nn/conv_gemm_halo.cu),
-    3 persistent in 2-CTA clusters with multicast weight tiles."""
+    3 persistent as CTA pairs (cta_group::2)."""
     if not use_persistent(persistent):
         return 0, pick_box(*out_nhw)
     env = os.environ.get("DDPT_GEMM_HALO", "1")
@@ -101,7 +103,7 @@ def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: in
         # padded rows); streamed weights make it lose to the plain persistent kernel, so those cases stay on mode 1
         if box is not None and (halo or (resident and eff >= 0.8)):
             return 2, box
-    return (3 if bn >= 128 and use_multicast(multicast) else 1), pick_box(*out_nhw)
+    return (3 if bn >= 128 and use_cta_pair(pair) else 1), pick_box(*out_nhw)
 
 
 def _block_n(n_total: int, prefer: Optional[int]) -> int:
@@ -127,7 +129,7 @@ def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Opt
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-             persistent: Optional[bool] = None, halo: Optional[bool] = None, multicast: Optional[bool] = None):
+             persistent: Optional[bool] = None, halo: Optional[bool] = None, pair: Optional[bool] = None):
     """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
     ext = require_native()
     n, h, w, c = x.shape
@@ -136,7 +138,7 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
     if out is None:
         out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
     bn = _block_n(c_out, block_n)
-    mode, box = (0, pick_box(n, ho, wo)) if split_k > 1 else _gemm_mode(persistent, halo, (n, ho, wo), kh, kw, c, c_out, bn, multicast)
+    mode, box = (0, pick_box(n, ho, wo)) if split_k > 1 else _gemm_mode(persistent, halo, (n, ho, wo), kh, kw, c, c_out, bn, pair)
     tiles = ext.conv_gemm(x, w_km, out.view(n * ho * wo, c_out), [n, ho, wo], list(box), [kh, kw], 1, [0, 0], False,
                           bias, relu, stat_partials, split_k, bn, mode)
     return out, tiles
@@ -144,7 +146,7 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
                block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None,
-               multicast: Optional[bool] = None):
+               pair: Optional[bool] = None):
     """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
@@ -153,7 +155,7 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
     if out is None:
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
     bn = _block_n(c_in, block_n)
-    mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, multicast)
+    mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, pair)
     ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
                   None, False, None, 1, bn, mode)
     return out
@@ -249,19 +251,19 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
                stat_partials: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split_k: int = 1,
-               block_n: Optional[int] = None, persistent: Optional[bool] = None, multicast: Optional[bool] = None):
+               block_n: Optional[int] = None, persistent: Optional[bool] = None, pair: Optional[bool] = None):
     """y [M, N] = x [M, K] @ w [N, K]^T (+ bias)."""
     m, k = x.shape
     y, tiles = conv_fwd(x.view(1, 1, m, k), w, 1, 1, bias, relu, stat_partials, None, block_n, out_dtype, split_k,
-                        persistent, None, multicast)
+                        persistent, None, pair)
     return y.view(m, w.shape[0]), tiles
 
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None,
-                 persistent: Optional[bool] = None, multicast: Optional[bool] = None):
+                 persistent: Optional[bool] = None, pair: Optional[bool] = None):
     """dx [M, K] = dy [M, N] @ w [N, K]."""
     m, n = dy.shape
-    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n, persistent, None, multicast).view(m, w.shape[1])
+    return conv_dgrad(dy.view(1, 1, m, n), w, 1, 1, None, block_n, persistent, None, pair).view(m, w.shape[1])
 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,

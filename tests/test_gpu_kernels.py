@@ -14,13 +14,13 @@ def ext():
     return ops.require_native()
 
 
-@pytest.fixture(params=["halo", "persistent", "multicast", "per_tile"], autouse=True)
+@pytest.fixture(params=["halo", "persistent", "pair", "per_tile"], autouse=True)
 def gemm_flavour(request, monkeypatch):
-    """Every GEMM/conv test runs against all forward/dgrad kernels (halo reuse, persistent, persistent in 2-CTA
-    clusters with multicast weight tiles, one CTA per tile)."""
+    """Every GEMM/conv test runs against all forward/dgrad kernels (halo reuse, persistent, persistent as CTA pairs
+    with cta_group::2 MMAs, one CTA per tile)."""
     monkeypatch.setenv("DDPT_GEMM_PERSISTENT", "0" if request.param == "per_tile" else "1")
     monkeypatch.setenv("DDPT_GEMM_HALO", "force" if request.param == "halo" else "0")
-    monkeypatch.setenv("DDPT_GEMM_MULTICAST", "1" if request.param == "multicast" else "0")
+    monkeypatch.setenv("DDPT_GEMM_PAIR", "1" if request.param == "pair" else "0")
     return request.param
 
 
