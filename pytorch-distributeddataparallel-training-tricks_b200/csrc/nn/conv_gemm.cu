@@ -102,14 +102,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===== TMA producer =====
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       const uint32_t tx_bytes = args.a_rows_bytes + kBStageBytes;
+      // (tap, channel chunk) of the K block advance with counters: divisions once, before the loop
+      int tap = kb_begin / args.k_chunks, chunk = kb_begin - tap * args.k_chunks;
+      int r = tap / args.taps_w, sx = tap - r * args.taps_w;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kStages;
         const uint32_t phase = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], phase ^ 1, 1);
         const int kb = kb_begin + i;
-        const int tap = kb / args.k_chunks;
-        const int chunk = kb - tap * args.k_chunks;
-        const int r = tap / args.taps_w, sx = tap - r * args.taps_w;
         mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
         tma_load_4d(smem_a + s * kAStageBytes, &tmap_a, &full_bar[s], chunk * kBlockK,
                     w0 + args.a_w_off + args.tap_sign * sx, h0 + args.a_h_off + args.tap_sign * r, n0);
@@ -121,6 +121,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_load_2d(smem_b + s * kBStageBytes + j * (kBlockK * 128), &tmap_b, &full_bar[s],
                         tap * args.n_total + col0 + j * 64, chunk * kBlockK);
         }
+        if (++chunk == args.k_chunks) { chunk = 0; ++tap; if (++sx == args.taps_w) { sx = 0; ++r; } }
       }
     }
   } else if (warp == 1) {
