@@ -95,6 +95,13 @@ void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bo
   ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, cur());
 }
 
+void chw_to_hwc(at::Tensor in, at::Tensor out, int64_t c, int64_t p) {
+  need(in, at::kBFloat16, "in"); need(out, at::kBFloat16, "out");
+  TORCH_CHECK(in.numel() == out.numel() && in.numel() % (c * p) == 0, "chw_to_hwc: [N, C*P] -> [N, P, C]");
+  c10::cuda::CUDAGuard g(in.device());
+  ddpt::launch_chw_to_hwc(bf(in), bfm(out), (int)(in.numel() / (c * p)), (int)c, (int)p, cur());
+}
+
 int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor partials, bool pool, bool flatten_chw) {
   need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
   need(partials, at::kFloat, "partials");
@@ -226,5 +233,6 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_finalize", &bn_bwd_finalize);
   m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("chw_to_hwc", &chw_to_hwc);
   m.def("head", &head);
 }

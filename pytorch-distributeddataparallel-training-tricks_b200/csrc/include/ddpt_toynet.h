@@ -53,6 +53,8 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                             const float* mean, const float* invstd, float* dgamma, float* dbeta,
                             float* coef /*[3][C]*/, int accumulate, cudaStream_t s);
+// [N][C][P] -> [N][P][C] bf16 (flatten order of the first Linear's data gradient -> channels-last)
+void launch_chw_to_hwc(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int c, int p, cudaStream_t s);
 // Pass 2: dy = c1 * (dz - c2 - xhat * c3) as bf16 NHWC; optionally sum dy per channel (conv bias gradient).
 void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
                          const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy,

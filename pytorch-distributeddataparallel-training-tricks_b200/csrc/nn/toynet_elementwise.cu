@@ -784,6 +784,40 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
 }
 
 // ================================================================================================
+// [N][C][P] -> [N][P][C] (bf16): the first Linear's data gradient arrives in torch's flatten order (c, h, w); the
+// pooled BatchNorm backward wants channels innermost.  One image per CTA through shared memory, 16-byte global
+// accesses on both sides.  ncu on the gather it replaces (8 strided 2-byte loads per window inside the BatchNorm
+// passes): 49.6 + 63.4 us at 1.7 TB/s for conv.10, long-scoreboard bound (profiles/ncu_bnbwd_v9.txt).
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads)
+chw_to_hwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c, int p) {
+  extern __shared__ __nv_bfloat16 s_tile[];                // [c][p + 2]
+  const int pitch = p + 2;
+  const int vec_per_img = c * p / 8;
+  for (int img = blockIdx.x; img < n; img += gridDim.x) {
+    const __nv_bfloat16* src = in + (size_t)img * c * p;
+    for (int i = threadIdx.x; i < vec_per_img; i += kThreads) {
+      const uint4 v = ldg16(src + (size_t)i * 8);
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+      const int flat = i * 8, ch = flat / p, pos = flat - ch * p;   // p % 8 == 0: one vector stays in one channel
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_tile[ch * pitch + pos + j] = e[j];
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = out + (size_t)img * c * p;
+    const int cv = c / 8;
+    for (int i = threadIdx.x; i < vec_per_img; i += kThreads) {
+      const int pos = i / cv, v = i - pos * cv;
+      __nv_bfloat16 e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[j] = s_tile[(v * 8 + j) * pitch + pos];
+      *reinterpret_cast<uint4*>(dst + (size_t)pos * c + v * 8) = *reinterpret_cast<const uint4*>(e);
+    }
+    __syncthreads();
+  }
+}
+
+// ================================================================================================
 // Head: Linear(512,10) + CE(mean)/B + argmax (+ backward)
 // ================================================================================================
 constexpr int kFeat = 512, kCls = 10, kHeadRows = 8;   // one warp per row, 8 rows per block iteration
@@ -994,6 +1028,15 @@ void launch_head(const HeadArgs& args, cudaStream_t s) {
   const int cap = sm_count();
   if (grid > cap) grid = cap;
   head_kernel<<<grid, kThreads, 0, s>>>(args);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_chw_to_hwc(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int c, int p, cudaStream_t s) {
+  if (p % 8 != 0 || c % 8 != 0) throw std::runtime_error("chw_to_hwc: C and H*W must be multiples of 8");
+  const size_t smem = (size_t)c * (p + 2) * sizeof(__nv_bfloat16);
+  if (smem > 48 * 1024) throw std::runtime_error("chw_to_hwc: one image does not fit 48 KiB of shared memory");
+  const int grid = n < 4 * sm_count() ? n : 4 * sm_count();
+  chw_to_hwc_kernel<<<grid, kThreads, smem, s>>>(in, out, n, c, p);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -99,9 +99,9 @@ def _gemm_mode(persistent: Optional[bool], halo: Optional[bool], out_nhw, kh: in
         max_rows = ((227 * 1024 - 2048 - b_bytes) // 3) // 128 if resident else 1 << 30
         box, eff = pick_box_halo(*out_nhw, kh, kw, max_rows)
         # measured (profiles/kernel_probe_b1024.json): the halo variant wins when the weights are resident (Toy_Net
-        # conv.3 forward 81 vs 128 us with exact 8-pixel tiling; conv.3 data gradient 177 vs 218 us even with 19 %
-        # padded rows); streamed weights make it lose to the plain persistent kernel, so those cases stay on mode 1
-        if box is not None and (halo or (resident and eff >= 0.8)):
+        # conv.3 forward 78 vs 115 us with exact 8-pixel tiling; conv.3 data gradient 176 vs 188 us even with a third
+        # of the MMA rows padding); streamed weights make it lose to the persistent kernel, so those stay on mode 1/3
+        if box is not None and (halo or (resident and eff >= 0.6)):
             return 2, box
     return (3 if bn >= 128 and use_cta_pair(pair) else 1), pick_box(*out_nhw)
 
@@ -239,8 +239,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
     else:
         box = pick_box(n, ho, wo, 16)
         ctas = (c_out // 128) * kh * kw * (c_in // bn)
-        if split_k is None:
-            split_k = max(1, min(bricks_of(box), -(-2 * sms // ctas)))
+        if split_k is None:      # the stage ring fills shared memory (one CTA per SM): fill one wave, never 2.07
+            split_k = max(1, min(bricks_of(box), sms // ctas))
     if out is None:
         out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
     elif not accumulate and slab is None and split_k > 1 and not out_is_zero:

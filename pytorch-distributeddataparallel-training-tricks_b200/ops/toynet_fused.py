@@ -60,6 +60,7 @@ class _Workspace:
                    e(batch, 512)]
         self.da = [e(batch, 26, 26, 64), e(batch, 12, 12, 128), e(batch, 10, 10, 256), e(batch, 8192),
                    e(batch, 512)]
+        self.da3_hwc = e(batch, 4, 4, 512)                 # da[3] (flatten order c,h,w) as channels-last
         self.saved_x: Optional[torch.Tensor] = None
         # block-scaled fp8 copies of the activations feeding conv.7, conv.10 and dense.1 ("O1-fp8")
         self.q = {}
@@ -246,12 +247,15 @@ class FusedToyNet:
         dy4 = ws.dy[4]
         off_critical_path(lambda: gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], out_is_zero=True))
         ready(16)
-        g = gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
-        g = ws.da[3]
+        gemm.conv_dgrad(dy4.view(1, 1, batch, 512), self._weight_bf16(16), 1, 1, ws.da[3].view(1, 1, batch, 8192))
+        # the Linear's data gradient is in flatten order (c, h, w); one 16 MB transpose (L2-resident input) lets the
+        # pooled BatchNorm passes read 16-byte channel vectors instead of gathering 2-byte elements (113 -> ~50 us)
+        ext.chw_to_hwc(ws.da[3], ws.da3_hwc, 512, 16)
+        g = ws.da3_hwc
         for k in (3, 2, 1):
             pidx, h_in, c_in, c_out, pool = _TC_BLOCKS[k - 1]
             h_out = h_in - 2
-            self._bn_backward(k, ws, g, grads, pool, k == 3, batch * float(h_out * h_out), dbias_idx=pidx + 1)
+            self._bn_backward(k, ws, g, grads, pool, False, batch * float(h_out * h_out), dbias_idx=pidx + 1)
             ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
             off_critical_path(lambda k=k, pidx=pidx: gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx],
                                                                      out_is_zero=True))
