@@ -225,7 +225,7 @@ def test_fused_lookahead_sgd_matches_eager(ext):
             continue
         oa.step(); ob.step()
         for pa, pb in zip(a.parameters(), b.parameters()):
-            torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(pa, pb, rtol=1e-4, atol=5e-6)
     st = fused.state.tolist()
     assert st[0] == 22 and st[1] == 22 % 10 and st[5] == 1
     # bf16 shadow tracks the master weights
