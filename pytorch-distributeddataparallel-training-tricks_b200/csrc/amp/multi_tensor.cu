@@ -48,6 +48,8 @@ __device__ __forceinline__ void apply_chunk(const float* __restrict__ a, const f
 template <typename Op>
 __global__ void __launch_bounds__(kThreads)
 multi_tensor_kernel(TensorList list, ChunkMap map, Op op, float* __restrict__ found_inf) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   const int total = map.first_chunk[map.count];
   bool bad = false;
   op.prepare();
@@ -102,6 +104,8 @@ int grid_for(int chunks) {
 
 __global__ void __launch_bounds__(kThreads)
 unscale_arena_kernel(float* __restrict__ g, long long n, float* __restrict__ state) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   const float inv = state[kInvScale];
   bool bad = false;
   const long long nv = n / 4;
@@ -121,6 +125,8 @@ unscale_arena_kernel(float* __restrict__ g, long long n, float* __restrict__ sta
 }
 
 __global__ void update_scale_kernel(float* __restrict__ s, int growth_interval, float min_scale, float max_scale) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float scale = s[kScale];
   if (s[kFoundInf] != 0.0f) {
@@ -146,7 +152,7 @@ void launch_multi_tensor_scale(const TensorList& list, const float* scale_ptr, f
   if (list.count == 0) return;
   ChunkMap map = build_map(list);
   ScaleOp op{scale_ptr, 1.0f};
-  multi_tensor_kernel<ScaleOp><<<grid_for(map.first_chunk[map.count]), kThreads, 0, stream>>>(list, map, op, found_inf);
+  launch_pdl(multi_tensor_kernel<ScaleOp>, dim3(grid_for(map.first_chunk[map.count])), dim3(kThreads), 0, stream, list, map, op, found_inf);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -155,7 +161,7 @@ void launch_multi_tensor_axpby(const TensorList& list, float a, float b, int arg
   if (list.count == 0) return;
   ChunkMap map = build_map(list);
   AxpbyOp op{a, b, arg_to_check};
-  multi_tensor_kernel<AxpbyOp><<<grid_for(map.first_chunk[map.count]), kThreads, 0, stream>>>(list, map, op, found_inf);
+  launch_pdl(multi_tensor_kernel<AxpbyOp>, dim3(grid_for(map.first_chunk[map.count])), dim3(kThreads), 0, stream, list, map, op, found_inf);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -163,13 +169,13 @@ void launch_unscale_arena(float* grads, long long n, float* scaler_state, cudaSt
   if (n <= 0) return;
   long long want = (n / 4 + kThreads - 1) / kThreads;
   int grid = (int)(want < (long long)sm_count() * 8 ? (want > 0 ? want : 1) : sm_count() * 8);
-  unscale_arena_kernel<<<grid, kThreads, 0, stream>>>(grads, n, scaler_state);
+  launch_pdl(unscale_arena_kernel, dim3(grid), dim3(kThreads), 0, stream, grads, n, scaler_state);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_update_scale(float* scaler_state, int growth_interval, float min_scale, float max_scale,
                          cudaStream_t stream) {
-  update_scale_kernel<<<1, 32, 0, stream>>>(scaler_state, growth_interval, min_scale, max_scale);
+  launch_pdl(update_scale_kernel, dim3(1), dim3(32), 0, stream, scaler_state, growth_interval, min_scale, max_scale);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -18,6 +18,8 @@ template <bool SRC_FP32>
 __global__ void __launch_bounds__(kThreads)
 quantize_mxfp8_kernel(const void* __restrict__ src, uint8_t* __restrict__ data, uint8_t* __restrict__ scale,
                       long long num_blocks) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   for (long long blk = (long long)blockIdx.x * kThreads + threadIdx.x; blk < num_blocks;
        blk += (long long)gridDim.x * kThreads) {
     float v[32];
@@ -74,8 +76,8 @@ void launch_quantize_mxfp8(const void* src, int src_is_fp32, uint8_t* data_out, 
   if (num_blocks <= 0) return;
   long long want = (num_blocks + kThreads - 1) / kThreads;
   const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
-  if (src_is_fp32) quantize_mxfp8_kernel<true><<<grid, kThreads, 0, stream>>>(src, data_out, scale_out, num_blocks);
-  else quantize_mxfp8_kernel<false><<<grid, kThreads, 0, stream>>>(src, data_out, scale_out, num_blocks);
+  if (src_is_fp32) launch_pdl(quantize_mxfp8_kernel<true>, dim3(grid), dim3(kThreads), 0, stream, src, data_out, scale_out, num_blocks);
+  else launch_pdl(quantize_mxfp8_kernel<false>, dim3(grid), dim3(kThreads), 0, stream, src, data_out, scale_out, num_blocks);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -1,4 +1,5 @@
 // Process-wide runtime helpers (error reporting, device properties).
+#include <cstdlib>
 #include "../include/ddpt_common.cuh"
 #include <cstdio>
 #include <stdexcept>
@@ -21,6 +22,15 @@ int sm_count() {
   DDPT_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
   if (dev < 64) cached[dev] = n;
   return n;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("DDPT_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached != 0;
 }
 
 }  // namespace ddpt

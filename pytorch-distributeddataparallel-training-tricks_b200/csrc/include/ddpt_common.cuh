@@ -17,6 +17,34 @@ namespace ddpt {
 void report_cuda_error(cudaError_t e, const char* expr, const char* file, int line);
 int sm_count();  // cached multiprocessor count of the current device
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of the training step is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_wait(): its CTAs may be scheduled (and run their parameter-only prologue: barrier init, TMEM allocation,
+// tensor-map prefetch) while the previous kernel of the stream drains, but touch global memory only after that
+// kernel has completed and flushed.  pdl_trigger() lets the NEXT kernel do the same.  Inside a CUDA graph the
+// edges become programmatic dependencies.  DDPT_PDL=0 launches without the attribute (then both are no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DDPT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+#endif
+
 // Loss-scaler state block shared by amp / all-reduce / optimizer kernels:
 //   [0] scale  [1] 1/scale  [2] found_inf (0/1)  [3] clean steps  [4] skipped steps
 enum ScalerSlot { kScale = 0, kInvScale = 1, kFoundInf = 2, kCleanSteps = 3, kSkipped = 4 };

@@ -97,6 +97,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // operands come from the previous kernel of the stream: wait for it only now, after the setup
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -289,7 +291,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   }
   const int tiles_m = a.tiles_w * a.tiles_h * tiles_n;
   dim3 grid(tiles_m, p.n_total / BN, p.split_k > 1 ? p.split_k : 1);
-  kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a);
+  launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_a, tmap_b, a);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return tiles_m;
 }

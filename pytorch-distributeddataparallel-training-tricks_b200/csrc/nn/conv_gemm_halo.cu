@@ -90,6 +90,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // operands come from the previous kernel of the stream: wait for it only now, after the setup
+  pdl_trigger();
 
   auto load_b = [&](uint8_t* dst, uint64_t* bar, int tap, int chunk, int col0) {
     if (!B_MN) {
@@ -373,7 +375,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   if (grid < tiles_n_cols) grid = tiles_n_cols;
   auto run = [&](auto kernel) {
     DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
+    launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
   };
   if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true>);
   else run(conv_gemm_halo_kernel<BN, B_MN, false>);

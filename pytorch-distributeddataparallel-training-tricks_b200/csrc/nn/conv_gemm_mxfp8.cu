@@ -111,6 +111,8 @@ conv_gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // operands come from the previous kernel of the stream: wait for it only now, after the setup
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -357,7 +359,7 @@ int launch_conv_gemm_mxfp8(const Mxfp8GemmProblem& p, cudaStream_t stream) {
   int grid = total_tiles < sm_count() ? total_tiles : sm_count();
   grid -= grid % tiles_n_cols;
   if (grid < tiles_n_cols) grid = tiles_n_cols;
-  conv_gemm_mxfp8_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
+  launch_pdl(conv_gemm_mxfp8_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return p.stat_partials != nullptr ? grid : tiles_m;
 }

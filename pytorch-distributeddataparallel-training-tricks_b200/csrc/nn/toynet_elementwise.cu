@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads)
 conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restrict__ weight,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ partials,
                  int batch) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
   __shared__ float s_red[2][kC0];
   const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
@@ -148,6 +150,8 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
 __global__ void __launch_bounds__(kThreads)
 conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16* __restrict__ dy,
                    float* __restrict__ dw, float* __restrict__ db, int batch) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
   __shared__ float s_acc[kC0 * 10];
   const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
@@ -219,6 +223,8 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    BnCoeffs out, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ nbt) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ double s_sum[kFinGroups][32], s_sq[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -270,6 +276,8 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                       int channels, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= channels) return;
   const float sc = gamma[c] * rsqrtf(rv[c] + eps);
@@ -284,6 +292,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
                     uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   constexpr int U = POOL ? 2 : 4;
   const int cv = c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
@@ -348,6 +358,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                             const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c,
                             uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ __nv_bfloat16 s_t[];                  // [c][ppix + 2] (padded)
   const int oh = h >> 1, ow = w >> 1, ppix = oh * ow, cv = c >> 3, ld = ppix + 2;
   const long long img = blockIdx.x;
@@ -473,6 +485,8 @@ __device__ __forceinline__ uint4 load_g_packed(const BwdCtx& k, int img, int ph,
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ float s_part[];                       // [2][c]
   const int cv = k.c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
@@ -597,6 +611,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
                        const float* __restrict__ gamma, const float* __restrict__ mean,
                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ coef, int accumulate) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ double s_a[kFinGroups][32], s_b[kFinGroups][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -639,6 +655,8 @@ template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                     float* __restrict__ dbias) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ float s_db[];                          // [c]
   const int cv = k.c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
@@ -791,6 +809,8 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads)
 chw_to_hwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c, int p) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ __nv_bfloat16 s_tile[];                // [c][p + 2]
   const int pitch = p + 2;
   const int vec_per_img = c * p / 8;
@@ -824,6 +844,8 @@ constexpr int kFeat = 512, kCls = 10, kHeadRows = 8;   // one warp per row, 8 ro
 
 __global__ void __launch_bounds__(kThreads)
 head_kernel(HeadArgs a) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_w[kCls][kFeat];
   __shared__ float s_dw[kCls][kFeat];
   __shared__ float s_db[kCls];
@@ -927,7 +949,7 @@ int conv0_partial_rows() { return sm_count() * 2; }
 int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const float* bias, __nv_bfloat16* y,
                      float* stat_partials, int batch, cudaStream_t s) {
   const int grid = batch < conv0_partial_rows() ? batch : conv0_partial_rows();
-  conv0_fwd_kernel<<<grid, kThreads, 0, s>>>(x, x_is_u8, weight, bias, y, stat_partials, batch);
+  launch_pdl(conv0_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, weight, bias, y, stat_partials, batch);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return grid;
 }
@@ -935,14 +957,14 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const floa
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
                         cudaStream_t s) {
   const int grid = batch < sm_count() * 2 ? batch : sm_count() * 2;
-  conv0_wgrad_kernel<<<grid, kThreads, 0, s>>>(x, x_is_u8, dy, dw, db, batch);
+  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, batch);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                         const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
                         float* running_var, long long* nbt, cudaStream_t s) {
-  bn_finalize_kernel<<<(channels + 31) / 32, 32 * kFinGroups, 0, s>>>(partials, num_partials, channels, count, gamma, beta,
+  launch_pdl(bn_finalize_kernel, dim3((channels + 31) / 32), dim3(32 * kFinGroups), 0, s, partials, num_partials, channels, count, gamma, beta,
                                                                 eps, momentum, out, running_mean, running_var, nbt);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -950,7 +972,7 @@ void launch_bn_finalize(const float* partials, int num_partials, int channels, d
 void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                            const float* running_var, float eps, int channels, float* scale, float* shift,
                            cudaStream_t s) {
-  bn_eval_coeffs_kernel<<<(channels + 127) / 128, 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, channels,
+  launch_pdl(bn_eval_coeffs_kernel, dim3((channels + 127) / 128), dim3(128), 0, s, gamma, beta, running_mean, running_var, eps, channels,
                                                                scale, shift);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -969,14 +991,14 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
     if (!pool) throw std::runtime_error("flatten_chw is only implemented together with the pool");
     const int ppix = (h / 2) * (w / 2);
     const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
-    bn_relu_pool_flatten_kernel<<<n, kThreads, smem, s>>>(y, scale, shift, out, h, w, c, q_out, q_scale);
+    launch_pdl(bn_relu_pool_flatten_kernel, dim3(n), dim3(kThreads), smem, s, y, scale, shift, out, h, w, c, q_out, q_scale);
   } else {
     const long long pixels = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
     const int rows_per_blk = kThreads / (c / 8);
     const int grid = persistent_grid(pixels, rows_per_blk * (pool ? 2 : 4), 8);
     if (q_out != nullptr && (c % 32 != 0)) throw std::runtime_error("MXFP8 side output needs C % 32 == 0");
-    if (pool) bn_relu_pool_kernel<true><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c, q_out, q_scale);
-    else bn_relu_pool_kernel<false><<<grid, kThreads, 0, s>>>(y, scale, shift, out, n, h, w, c, q_out, q_scale);
+    if (pool) launch_pdl(bn_relu_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale);
+    else launch_pdl(bn_relu_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale);
   }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -993,8 +1015,8 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   long long want = (pix + rows_per_blk - 1) / rows_per_blk;
   const int grid = (int)(want < bn_bwd_partial_rows() ? want : bn_bwd_partial_rows());
   const size_t smem = 2 * c * sizeof(float);
-  if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(k, partials);
-  else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(k, partials);
+  if (pool) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, partials);
+  else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, partials);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return grid;
 }
@@ -1002,7 +1024,7 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                             const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
                             int accumulate, cudaStream_t s) {
-  bn_bwd_finalize_kernel<<<(channels + 31) / 32, 32 * kFinGroups, 0, s>>>(partials, num_partials, channels, count, gamma,
+  launch_pdl(bn_bwd_finalize_kernel, dim3((channels + 31) / 32), dim3(32 * kFinGroups), 0, s, partials, num_partials, channels, count, gamma,
                                                                     mean, invstd, dgamma, dbeta, coef, accumulate);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -1018,8 +1040,8 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   const int cap = sm_count() * 8;
   const int grid = (int)(want < cap ? want : cap);
   const size_t smem = c * sizeof(float);
-  if (pool) bn_bwd_apply_kernel<true><<<grid, kThreads, smem, s>>>(k, coef, dy, dbias);
-  else bn_bwd_apply_kernel<false><<<grid, kThreads, smem, s>>>(k, coef, dy, dbias);
+  if (pool) launch_pdl(bn_bwd_apply_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
+  else launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1027,7 +1049,7 @@ void launch_head(const HeadArgs& args, cudaStream_t s) {
   int grid = (args.batch + kHeadRows - 1) / kHeadRows;
   const int cap = sm_count();
   if (grid > cap) grid = cap;
-  head_kernel<<<grid, kThreads, 0, s>>>(args);
+  launch_pdl(head_kernel, dim3(grid), dim3(kThreads), 0, s, args);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1036,7 +1058,7 @@ void launch_chw_to_hwc(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int c
   const size_t smem = (size_t)c * (p + 2) * sizeof(__nv_bfloat16);
   if (smem > 48 * 1024) throw std::runtime_error("chw_to_hwc: one image does not fit 48 KiB of shared memory");
   const int grid = n < 4 * sm_count() ? n : 4 * sm_count();
-  chw_to_hwc_kernel<<<grid, kThreads, smem, s>>>(in, out, n, c, p);
+  launch_pdl(chw_to_hwc_kernel, dim3(grid), dim3(kThreads), smem, s, in, out, n, c, p);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

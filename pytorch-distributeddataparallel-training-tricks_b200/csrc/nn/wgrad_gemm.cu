@@ -83,6 +83,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // operands come from the previous kernel of the stream: wait for it only now, after the setup
+  pdl_trigger();
 
   if (warp == 0) {
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
@@ -205,7 +207,7 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid(p.m_total / kBlockM, a.num_taps * (p.c_total / BN), p.split_k > 1 ? p.split_k : 1);
-  kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_dy, tmap_x, a);
+  launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_dy, tmap_x, a);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

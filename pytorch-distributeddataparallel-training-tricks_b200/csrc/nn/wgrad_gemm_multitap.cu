@@ -97,6 +97,8 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // operands come from the previous kernel of the stream: wait for it only now, after the setup
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer: dY brick + X halo brick per reduction step =====
@@ -244,6 +246,8 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __global__ void __launch_bounds__(256)
 reduce_slabs_kernel(const float4* __restrict__ slab, float4* __restrict__ out, long long nvec, int splits,
                     int accumulate) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
     float4 acc = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
@@ -341,7 +345,7 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   const int cols = max_group_taps * BN;
   auto run = [&](auto kernel) {
     DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_dy, tmap_x[0], tmap_x[1], a);
+    launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_dy, tmap_x[0], tmap_x[1], a);
   };
   if (cols <= 64) run(wgrad_multitap_kernel<BN, 64>);
   else if (cols <= 128) run(wgrad_multitap_kernel<BN, 128>);
@@ -352,7 +356,7 @@ void launch_impl(const WgradProblem& p, cudaStream_t stream) {
     const long long nvec = a.slab_elems / 4;
     long long want = (nvec + 255) / 256;
     const int blocks = (int)std::min<long long>(want, (long long)sm_count() * 8);
-    reduce_slabs_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(p.slab),
+    launch_pdl(reduce_slabs_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(p.slab),
                                                     reinterpret_cast<float4*>(p.dw), nvec, (int)grid.z, p.accumulate);
     DDPT_CUDA_CHECK(cudaGetLastError());
   }

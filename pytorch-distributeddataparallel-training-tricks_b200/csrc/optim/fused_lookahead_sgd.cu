@@ -41,6 +41,8 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* dst, float4 v) {
 
 __global__ void __launch_bounds__(kThreads)
 fused_lookahead_sgd_kernel(FusedSgdArgs a) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   if (a.found_inf != nullptr && *a.found_inf != 0.0f) {
     if (blockIdx.x == 0 && threadIdx.x == 0) a.state[kSkippedSteps] += 1;
     return;  // overflow: skip the whole step, counters included (uniform across the grid)
@@ -124,6 +126,8 @@ fused_lookahead_sgd_kernel(FusedSgdArgs a) {
 
 __global__ void __launch_bounds__(kThreads)
 cast_bf16_kernel(const float4* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec) {
+  pdl_wait();      // previous kernel of the stream has completed and flushed
+  pdl_trigger();   // the next kernel may be scheduled behind this one
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads)
     st_bf16x4(dst + 4 * i, src[i]);
 }
@@ -136,7 +140,7 @@ void launch_fused_lookahead_sgd(const FusedSgdArgs& args, cudaStream_t stream) {
   long long want = (nvec + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll);
   const int cap = sm_count() * 4;
   const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  fused_lookahead_sgd_kernel<<<grid, kThreads, 0, stream>>>(args);
+  launch_pdl(fused_lookahead_sgd_kernel, dim3(grid), dim3(kThreads), 0, stream, args);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -145,7 +149,7 @@ void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long numel, cud
   if (nvec <= 0) return;
   long long want = (nvec + kThreads - 1) / kThreads;
   const int cap = sm_count() * 8;
-  cast_bf16_kernel<<<(int)(want < cap ? want : cap), kThreads, 0, stream>>>(
+  launch_pdl(cast_bf16_kernel, dim3((int)(want < cap ? want : cap)), dim3(kThreads), 0, stream, 
       reinterpret_cast<const float4*>(src), dst, nvec);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
