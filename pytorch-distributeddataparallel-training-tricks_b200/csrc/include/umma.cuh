@@ -178,6 +178,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// Same descriptor, operand start moved by `byte_off` (a multiple of 16 that stays inside the 256 KiB window): one
+// add on the low word instead of re-encoding.  The MMA-issuing lane is a single in-order thread; with 64-column
+// tiles an MMA is only 32 tensor cycles, so ~10 uniform instructions of shift/mask/or per descriptor made the ISSUE
+// rate, not the tensor pipe, the limit (71 cycles per MMA measured on conv.3's data gradient).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_off) {
+  const uint32_t lo = static_cast<uint32_t>(desc) + (byte_off >> 4);
+  return (desc & 0xFFFFFFFF00000000ull) | lo;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                      // c_format  = F32

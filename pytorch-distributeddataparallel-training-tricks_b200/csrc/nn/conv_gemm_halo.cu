@@ -181,13 +181,13 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 b_addr = smem_u32(smem_b + sb * kBStageBytes);
               }
               const uint32_t a_view = a_addr + (dr * args.box_n) * 1024;     // whole swizzle atoms: aligned view
+              const uint64_t adesc0 = make_smem_desc(a_view, 0, 1024);
+              const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr, kBlockK * 128, 1024) : make_smem_desc(b_addr, 0, 1024);
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint64_t adesc = make_smem_desc(a_view + k * (kUmmaK * 2), 0, 1024);
-                const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
-                                            : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
-                mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (chunk | cs | dr | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                mma_bf16_ss(tmem_d, desc_advance(adesc0, k * (kUmmaK * 2)),
+                            desc_advance(bdesc0, k * (B_MN ? kUmmaK * 128 : kUmmaK * 2)), kIdesc,
+                            (chunk | cs | dr | k) != 0 ? 1u : 0u);
               if (!B_RES) mma_commit(&b_empty[sb]);
             }
             mma_commit(&a_empty[sa]);

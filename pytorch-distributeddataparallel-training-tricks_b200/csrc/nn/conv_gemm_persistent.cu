@@ -218,11 +218,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             const uint32_t a_addr = smem_u32(smem_a + s * a_stage_bytes + j * kAStageBytes);
             const uint32_t b_addr = B_RES ? smem_u32(smem_b + kb * kBStageBytes)
                                           : smem_u32(smem_b + s * b_stage_bytes + j * kBStageBytes);
+            const uint64_t adesc0 = make_smem_desc(a_addr, 0, 1024);
+            const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr, kBlockK * 128, 1024) : make_smem_desc(b_addr, 0, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 2), 0, 1024);
-              const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024)
-                                          : make_smem_desc(b_addr + k * (kUmmaK * 2), 0, 1024);
+              const uint64_t adesc = desc_advance(adesc0, k * (kUmmaK * 2));
+              const uint64_t bdesc = desc_advance(bdesc0, k * (B_MN ? kUmmaK * 128 : kUmmaK * 2));
               if (MC > 1) mma_bf16_ss_pair(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
               else mma_bf16_ss(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
             }

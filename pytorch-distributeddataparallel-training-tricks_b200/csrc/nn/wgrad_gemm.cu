@@ -127,10 +127,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + kABlocks * args.slot_bytes;
-        for (int k = 0; k < k_steps; ++k) {
-          const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_bytes, 1024);
-          const uint64_t bdesc = make_smem_desc(b_addr + k * (kUmmaK * 128), args.slot_bytes, 1024);
+        uint64_t adesc = make_smem_desc(a_addr, args.slot_bytes, 1024);
+        uint64_t bdesc = make_smem_desc(b_addr, args.slot_bytes, 1024);
+        for (int k = 0; k < k_steps; ++k) {               // 16 pixels further per step: one add per descriptor
           mma_bf16_ss(tmem_base, adesc, bdesc, kIdesc, (i | k) != 0 ? 1u : 0u);
+          adesc = desc_advance(adesc, kUmmaK * 128);
+          bdesc = desc_advance(bdesc, kUmmaK * 128);
         }
         mma_commit(&empty_bar[s]);
       }

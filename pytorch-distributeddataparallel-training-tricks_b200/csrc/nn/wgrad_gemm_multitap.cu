@@ -157,16 +157,19 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
           // K step k covers the 8-pixel groups 2k, 2k+1 of the brick: (row, column group) advance with counters --
           // a runtime division per MMA on the issuing lane costs more than the MMA itself
           int row = 0, cg = 0;
+          uint64_t adesc = make_smem_desc(a_addr, args.slot_a, 1024);
+          uint64_t bdesc0[kBBlocks];
+#pragma unroll
+          for (int blk = 0; blk < kBBlocks; ++blk) bdesc0[blk] = make_smem_desc(x_addr + blk * args.slot_x, tap_pitch, sbo_x);
           for (int k = 0; k < k_steps; ++k) {
             const uint32_t x_off = (row * xw + cg * 8) * 128;
             cg += 2;
             while (cg >= gpr) { cg -= gpr; ++row; }
-            const uint64_t adesc = make_smem_desc(a_addr + k * (kUmmaK * 128), args.slot_a, 1024);
 #pragma unroll
-            for (int blk = 0; blk < kBBlocks; ++blk) {
-              const uint64_t bdesc = make_smem_desc(x_addr + blk * args.slot_x + x_off, tap_pitch, sbo_x);
-              mma_bf16_ss(tmem_base + blk * 64 * box_taps, adesc, bdesc, idesc_wide, (i | k) != 0 ? 1u : 0u);
-            }
+            for (int blk = 0; blk < kBBlocks; ++blk)
+              mma_bf16_ss(tmem_base + blk * 64 * box_taps, adesc, desc_advance(bdesc0[blk], x_off), idesc_wide,
+                          (i | k) != 0 ? 1u : 0u);
+            adesc = desc_advance(adesc, kUmmaK * 128);
           }
         } else {
           int acc_idx = 0, dr = 0, ds = 0;
