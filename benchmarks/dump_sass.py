@@ -20,8 +20,13 @@ for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.*.o"))):
         short = re.sub(r"\(.*", "", short).replace("ddpt::", "")
         ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", f, flags=re.M)
         cnt = collections.Counter(o.split(".")[0] for o in ops)
-        rows.append((src, short, len(ops), {k: cnt[k] for k in KEY if cnt[k]}))
-        keep = ("conv_gemm_persistent_kernel<256, false, false>", "conv_gemm_halo_kernel<128, false, true>",
+        found = {k: cnt[k] for k in KEY if cnt[k]}
+        pair = sum(1 for o in ops if ".2CTA" in o)           # cta_group::2 forms (UTCHMMA.2CTA, UTMALDG.*.2CTA, ...)
+        if pair:
+            found["*.2CTA"] = pair
+        pdl = sum(1 for o in ops if o.startswith("ACQBULK") or o.startswith("PREEXIT"))
+        rows.append((src, short, len(ops), found))
+        keep = ("conv_gemm_persistent_kernel<256, false, false, 2>", "conv_gemm_halo_kernel<128, false, true>",
                 "wgrad_gemm_kernel<128>", "wgrad_multitap_kernel<64, 256>", "conv_gemm_mxfp8_kernel",
                 "fused_allreduce_kernel<3>", "fused_allreduce_kernel<2>", "fused_lookahead_sgd_kernel")
         if short in keep:     # full listings only for one representative of every kernel family (the rest: SUMMARY.md)
@@ -32,7 +37,8 @@ with open(os.path.join(OUT, "SUMMARY.md"), "w") as fh:
     fh.write("# SASS evidence (cuobjdump -sass of the in-tree sm_100a objects)\n\n"
              "`UTCHMMA` = tcgen05.mma (kind::f16), `UTMALDG` = TMA tensor load, `LDTM` = tcgen05.ld, "
              "`UTCBAR` = tcgen05.commit, `UTCATOMSWS` = TMEM alloc, `SYNCS` = mbarrier ops, "
-             "`LDGMC` = multimem.ld_reduce, `REDG` = red.global, `ATOMG` = system-scope CAS flags.\n\n"
+             "`LDGMC` = multimem.ld_reduce, `REDG` = red.global, `ATOMG` = system-scope CAS flags, "
+             "`*.2CTA` = cta_group::2 forms (paired MMA, pair TMA loads, multicast commit, pair TMEM alloc).\n\n"
              "| source | kernel | SASS instrs | key mnemonics |\n|---|---|---|---|\n")
     for src, short, n, c in rows:
         fh.write(f"| `{src}` | `{short[:70]}` | {n} | {', '.join(f'{k}x{v}' for k, v in c.items())} |\n")
