@@ -1,5 +1,6 @@
 """Fused Toy_Net (sm_100a) vs the plain PyTorch fp32 graph: forward, backward, training, engine."""
 import copy
+import os
 
 import pytest
 import torch
@@ -200,3 +201,29 @@ def test_fp8_block_scaled_forward_path_trains():
     hist = [iterate_loader(loader, model, loss_fn, 0, opt, training=True)[0] for _ in range(3)]
     assert hist[-1] < hist[0] * 0.75, hist
     amp.reset()
+
+
+def test_chw_to_hwc_and_gemm_dispatch():
+    """The flatten-order -> channels-last transpose ahead of conv.10's BatchNorm backward, and which GEMM kernel each
+    Toy_Net layer is routed to by default (persistent / halo reuse / CTA pair)."""
+    from ddpt_b200 import ops
+    from ddpt_b200.ops import gemm
+    ext = ops.require_native()
+    for n, c, p in ((3, 512, 16), (1024, 512, 16), (5, 64, 8)):
+        x = torch.randn(n, c * p, device="cuda").bfloat16()
+        out = torch.empty(n, p, c, device="cuda", dtype=torch.bfloat16)
+        ext.chw_to_hwc(x, out, c, p)
+        assert torch.equal(out, x.view(n, c, p).transpose(1, 2).contiguous())
+    env = {k: os.environ.pop(k, None) for k in ("DDPT_GEMM_PAIR", "DDPT_GEMM_HALO", "DDPT_GEMM_PERSISTENT")}
+    try:
+        B = 1024
+        mode = lambda nhw, ck, n, bn: gemm._gemm_mode(None, None, nhw, 3, 3, ck, n, bn)[0]
+        assert mode((B, 24, 24), 64, 128, 128) == 2       # conv.3 forward: resident weights, halo reuse
+        assert mode((B, 26, 26), 128, 64, 64) == 2        # conv.3 data gradient: halo reuse
+        assert mode((B, 10, 10), 128, 256, 256) == 3      # conv.7 forward: CTA pair
+        assert mode((B, 8, 8), 256, 512, 256) == 3        # conv.10 forward: CTA pair
+        assert mode((B, 12, 12), 256, 128, 128) == 3      # conv.7 data gradient: CTA pair
+    finally:
+        for k, v in env.items():
+            if v is not None:
+                os.environ[k] = v
