@@ -57,6 +57,11 @@ class StepEngine:
         self.host_metrics_every_step = False
         self._host_ring = torch.zeros((1024, 2), dtype=torch.float32).pin_memory()
         self._host_slot = 0
+        # host batches are staged through two device buffers on a copy stream, so the H2D transfer of step i+1
+        # overlaps the compute of step i (the graph's input buffer is then filled by a ~1 us device-to-device copy)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, Optional[torch.cuda.Event]]] = {}
+        self._stage_slot = 0
 
     # -- eligibility ---------------------------------------------------------------------------------
     def accepts(self, model, loss_function, optimizer, training: bool) -> bool:
@@ -143,8 +148,30 @@ class StepEngine:
                 self._static[batch] = (sx, st)
                 self._graphs.pop(key, None)
                 self._seen[key] = 0
-        sx.copy_(image.reshape(sx.shape), non_blocking=True)
-        st.copy_(target, non_blocking=True)
+        if image.device.type == "cpu" and target.device.type == "cpu":
+            slot = self._stage_slot
+            self._stage_slot ^= 1
+            entry = self._stage.get((batch, slot))
+            if entry is None or entry[0].dtype != sx.dtype:
+                entry = (torch.empty_like(sx), torch.empty_like(st), None)
+            gx, gt, free = entry
+            main = torch.cuda.current_stream(self.device)
+            if free is not None:
+                self.copy_stream.wait_event(free)          # the compute stream has consumed this slot (2 steps ago)
+            with torch.cuda.stream(self.copy_stream):
+                gx.copy_(image.reshape(sx.shape), non_blocking=True)
+                gt.copy_(target, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self.copy_stream)
+            main.wait_event(landed)
+            sx.copy_(gx, non_blocking=True)
+            st.copy_(gt, non_blocking=True)
+            consumed = torch.cuda.Event()
+            consumed.record(main)
+            self._stage[(batch, slot)] = (gx, gt, consumed)
+        else:
+            sx.copy_(image.reshape(sx.shape), non_blocking=True)
+            st.copy_(target, non_blocking=True)
         body = self._train_body if training else self._eval_body
         seen = self._seen.get(key, 0)
         graph = self._graphs.get(key)

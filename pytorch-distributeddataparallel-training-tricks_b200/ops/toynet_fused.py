@@ -93,7 +93,8 @@ class FusedToyNet:
         """Kernels of ours in one training step (forward + backward + unscale + scale update + optimizer)."""
         fwd = 1 + 1 + 1 + 3 * 3 + 3              # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio (head: in bwd)
         bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
-        return fwd + bwd + 3
+        bwd += 1 + 2                             # flatten -> channels-last transpose | split-K slab reductions (conv.3, conv.10 wgrad)
+        return fwd + bwd + 3                     # + unscale, scale update, optimizer (profiles/launches_step_b1024_v9.txt)
 
     # -- helpers ------------------------------------------------------------------------------------
     def workspace(self, batch: int) -> _Workspace:
