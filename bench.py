@@ -256,7 +256,9 @@ def run_ours(args):
                        "l2": "per-step working set > 1 GB of activations (>> 126 MB L2); 8 input batches cycled"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "final_loss": loss, "final_acc": acc},
+                    "d2h_bytes_per_step": d2h, "final_loss": loss, "final_acc": acc,
+                    "note": "separately timed loop through iterate_loader(): K distinct pinned host batches, H2D on a "
+                            "copy stream (overlaps the previous step), per-step async D2H of loss/acc"},
             "gpu_launches": int(launches_per_step * K),
             "graph_replays": int(replays),
             "published_baseline_note": "reference publishes no throughput; ~17.5k img/s derived from its logs on 2x RTX 2080",
