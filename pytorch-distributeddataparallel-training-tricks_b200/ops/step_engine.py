@@ -51,6 +51,11 @@ class StepEngine:
         import os
         self.wgrad_stream = (torch.cuda.Stream(device=self.device)
                              if os.environ.get("DDPT_WGRAD_STREAM", "1") != "0" else None)
+        # the graph is captured on a high-priority stream: the critical path (forward, data gradients, BatchNorm
+        # passes) is scheduled ahead of the side-stream weight gradients and bucket all-reduces whenever both have
+        # CTAs ready (DDPT_MAIN_PRIORITY=0 captures on torch's default capture stream)
+        self.capture_stream = (torch.cuda.Stream(device=self.device, priority=-1)
+                               if os.environ.get("DDPT_MAIN_PRIORITY", "1") != "0" else None)
         self.kernel_launches_per_step: Dict[Tuple[int, bool], int] = {}
         self.graph_replays = 0
         # optional: copy the metric accumulators to pinned host memory after every step (async, no sync)
@@ -187,7 +192,7 @@ class StepEngine:
                 self.fused_opt.prepare_for_capture(self.sgd, self.lookahead)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self.capture_stream):
                 body(sx, st)
             self._graphs[key] = graph
             graph.replay()
