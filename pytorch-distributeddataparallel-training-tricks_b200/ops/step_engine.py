@@ -51,11 +51,11 @@ class StepEngine:
         import os
         self.wgrad_stream = (torch.cuda.Stream(device=self.device)
                              if os.environ.get("DDPT_WGRAD_STREAM", "1") != "0" else None)
-        # the graph is captured on a high-priority stream: the critical path (forward, data gradients, BatchNorm
-        # passes) is scheduled ahead of the side-stream weight gradients and bucket all-reduces whenever both have
-        # CTAs ready (DDPT_MAIN_PRIORITY=0 captures on torch's default capture stream)
+        # DDPT_MAIN_PRIORITY=1 captures the graph on a high-priority stream (critical path ahead of the side-stream
+        # weight gradients).  Measured slower on the same box (1.673 vs 1.638 ms/step): with equal priorities the
+        # weight-gradient GEMMs start earlier and fill the SMs the bandwidth-bound passes leave idle.  Off by default.
         self.capture_stream = (torch.cuda.Stream(device=self.device, priority=-1)
-                               if os.environ.get("DDPT_MAIN_PRIORITY", "1") != "0" else None)
+                               if os.environ.get("DDPT_MAIN_PRIORITY", "0") == "1" else None)
         self.kernel_launches_per_step: Dict[Tuple[int, bool], int] = {}
         self.graph_replays = 0
         # optional: copy the metric accumulators to pinned host memory after every step (async, no sync)
