@@ -243,7 +243,9 @@ class FusedToyNet:
                  grads[21], dlogits, float(batch))
         ready(21); ready(20)
         # BN1d backward -> dy4
-        self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=17)
+        # biases in front of a BatchNorm (dense.1, conv.3/7/10) have an identically zero gradient: their slots keep
+        # the zero the gradient buffers are cleared to, and the apply pass skips the per-channel sum (dbias_idx=None)
+        self._bn_backward(4, ws, ws.da[4], grads, False, False, float(batch), dbias_idx=None)
         ready(19); ready(18); ready(17)
         dy4 = ws.dy[4]
         off_critical_path(lambda: gemm.linear_wgrad(dy4, ws.a[3], out=grads[16], out_is_zero=True))
@@ -256,7 +258,7 @@ class FusedToyNet:
         for k in (3, 2, 1):
             pidx, h_in, c_in, c_out, pool = _TC_BLOCKS[k - 1]
             h_out = h_in - 2
-            self._bn_backward(k, ws, g, grads, pool, False, batch * float(h_out * h_out), dbias_idx=pidx + 1)
+            self._bn_backward(k, ws, g, grads, pool, False, batch * float(h_out * h_out), dbias_idx=None)
             ready(pidx + 3); ready(pidx + 2); ready(pidx + 1)
             off_critical_path(lambda k=k, pidx=pidx: gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx],
                                                                      out_is_zero=True))
