@@ -79,14 +79,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// L2 prefetch of a box (no shared-memory destination, no barrier): issued a tile ahead by the producer lane, it turns
-// the later TMA load's HBM round trip into an L2 hit when the stage ring is too shallow to cover DRAM latency.
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 // CTA-pair forms (cta_group::2): each CTA of the pair loads into its OWN shared memory, but the bytes complete on
 // the LEADER's mbarrier (bit 24 of a shared::cluster address selects the CTA of the pair; clearing it names rank 0),
 // because only the leader issues the paired tcgen05.mma that consumes both halves.

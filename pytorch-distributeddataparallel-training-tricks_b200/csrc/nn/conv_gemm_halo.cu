@@ -120,20 +120,11 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int th = (tile_m / args.tiles_w) % args.tiles_h;
         const int tn = tile_m / (args.tiles_w * args.tiles_h);
         const int w0 = tw * 8, h0 = th * args.box_h, n0 = tn * args.box_n;
-        // the same bricks of this CTA's NEXT tile, prefetched into L2 while this tile streams: with resident weights
-        // only ~5 bricks fit the ring, about one HBM round trip (ncu: MMA lane waiting on a_full, tensor pipe 39 %)
-        const int tile_nx = tile + gridDim.x;
-        const bool has_nx = tile_nx < num_tiles;
-        const int tm_nx = tile_nx / num_n_tiles;
-        const int w0n = (tm_nx % args.tiles_w) * 8, h0n = ((tm_nx / args.tiles_w) % args.tiles_h) * args.box_h;
-        const int n0n = (tm_nx / (args.tiles_w * args.tiles_h)) * args.box_n;
         for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
           for (int cs = 0; cs < args.taps_w; ++cs) {       // one activation brick per filter column
             const int sa = a_s;
             const uint32_t a_ph = a_phase;
             if (++a_s == args.a_stages) { a_s = 0; a_phase ^= 1; }
-            if (has_nx)
-              tma_prefetch_4d(&tmap_a, chunk * kBlockK, w0n + args.org_w_off + cs, n0n, h0n + args.org_h_off);
             mbar_wait(&a_empty[sa], a_ph ^ 1, 41);
             mbar_arrive_expect_tx(&a_full[sa], args.a_tile_bytes);
             tma_load_4d(smem_a + sa * args.a_slot_bytes, &tmap_a, &a_full[sa], chunk * kBlockK,
