@@ -217,7 +217,6 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
 // ================================================================================================
 // One block per 32 channels; 8 row-groups of 32 lanes walk the partial rows (coalesced across channels).
 constexpr int kFinGroups = 32;                       // row groups per block in the *_finalize kernels
-constexpr int kFinUnroll = 8;                        // partial rows a thread has in flight per trip
 
 __global__ void __launch_bounds__(32 * kFinGroups)
 bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
@@ -231,20 +230,22 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
   const int c = blockIdx.x * 32 + lane;
   double sum = 0.0, sq = 0.0;
   if (c < channels) {
-    // kFinUnroll row groups per trip, masked instead of a scalar tail: the kernel is a chain of dependent L2 round
-    // trips (592 partial rows / 32 groups = 19 rows per thread: 3 trips instead of 4 + 3 single-row trips)
+    // 4 row groups per trip with independent accumulators: the loads of a trip are all in flight together
     double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int p = grp; p < num_partials; p += kFinUnroll * kFinGroups) {
-      float a[kFinUnroll], b[kFinUnroll];
+    int p = grp;
+    for (; p + 3 * kFinGroups < num_partials; p += 4 * kFinGroups) {
+      float a[4], b[4];
 #pragma unroll
-      for (int u = 0; u < kFinUnroll; ++u) {
-        const int row = p + u * kFinGroups;
-        const bool ok = row < num_partials;
-        a[u] = ok ? partials[((size_t)row * 2) * channels + c] : 0.f;
-        b[u] = ok ? partials[((size_t)row * 2 + 1) * channels + c] : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        a[u] = partials[((size_t)(p + u * kFinGroups) * 2) * channels + c];
+        b[u] = partials[((size_t)(p + u * kFinGroups) * 2 + 1) * channels + c];
       }
 #pragma unroll
-      for (int u = 0; u < kFinUnroll; ++u) { s4[u & 3] += (double)a[u]; q4[u & 3] += (double)b[u]; }
+      for (int u = 0; u < 4; ++u) { s4[u] += (double)a[u]; q4[u] += (double)b[u]; }
+    }
+    for (; p < num_partials; p += kFinGroups) {
+      s4[0] += (double)partials[((size_t)p * 2) * channels + c];
+      q4[0] += (double)partials[((size_t)p * 2 + 1) * channels + c];
     }
     sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
@@ -618,17 +619,20 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
   double a = 0.0, b = 0.0;
   if (c < channels) {
     double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int p = grp; p < num_partials; p += kFinUnroll * kFinGroups) {
-      float x[kFinUnroll], y[kFinUnroll];
+    int p = grp;
+    for (; p + 3 * kFinGroups < num_partials; p += 4 * kFinGroups) {
+      float x[4], y[4];
 #pragma unroll
-      for (int u = 0; u < kFinUnroll; ++u) {
-        const int row = p + u * kFinGroups;
-        const bool ok = row < num_partials;
-        x[u] = ok ? partials[((size_t)row * 2) * channels + c] : 0.f;
-        y[u] = ok ? partials[((size_t)row * 2 + 1) * channels + c] : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        x[u] = partials[((size_t)(p + u * kFinGroups) * 2) * channels + c];
+        y[u] = partials[((size_t)(p + u * kFinGroups) * 2 + 1) * channels + c];
       }
 #pragma unroll
-      for (int u = 0; u < kFinUnroll; ++u) { a4[u & 3] += (double)x[u]; b4[u & 3] += (double)y[u]; }
+      for (int u = 0; u < 4; ++u) { a4[u] += (double)x[u]; b4[u] += (double)y[u]; }
+    }
+    for (; p < num_partials; p += kFinGroups) {
+      a4[0] += (double)partials[((size_t)p * 2) * channels + c];
+      b4[0] += (double)partials[((size_t)p * 2 + 1) * channels + c];
     }
     a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
