@@ -1016,7 +1016,9 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
   const int rows_per_blk = kThreads / (c / 8);
   long long want = (pix + rows_per_blk - 1) / rows_per_blk;
-  const int grid = (int)(want < bn_bwd_partial_rows() ? want : bn_bwd_partial_rows());
+  // one resident wave (2 CTAs per SM at 128 registers): half the partial rows for bn_bwd_finalize to fold
+  const int cap = sm_count() * 2;
+  const int grid = (int)(want < cap ? want : cap);
   const size_t smem = 2 * c * sizeof(float);
   if (pool) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, partials);
   else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, partials);
