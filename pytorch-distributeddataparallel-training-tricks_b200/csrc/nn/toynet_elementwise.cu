@@ -13,6 +13,7 @@
 #include "../include/ddpt_toynet.h"
 #include "../include/ddpt_common.cuh"
 #include <cuda_fp8.h>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace ddpt {
@@ -1042,7 +1043,15 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
   const int rows_per_blk = kThreads / (c / 8);
   long long want = (pix + rows_per_blk - 1) / rows_per_blk;
-  const int cap = sm_count() * 8;
+  // CTAs per SM in the grid (2 are resident at a time).  Same-box A/B, 300 steps each: 8 per SM 1.568 / 1.560 ms,
+  // 2 per SM (one wave) 1.573 / 1.572 ms -- short CTAs leave gaps the side-stream weight gradients fill.
+  // DDPT_BN_APPLY_CTAS overrides.
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = std::getenv("DDPT_BN_APPLY_CTAS");
+    per_sm = e != nullptr && std::atoi(e) > 0 ? std::atoi(e) : 8;
+  }
+  const int cap = sm_count() * per_sm;
   const int grid = (int)(want < cap ? want : cap);
   const size_t smem = c * sizeof(float);
   if (dbias != nullptr) {
