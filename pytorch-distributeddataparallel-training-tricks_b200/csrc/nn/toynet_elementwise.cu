@@ -796,13 +796,15 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       *reinterpret_cast<uint4*>(dy + pix * k.c + v * 8) = pack8(o);
     }
   }
-  if (!HAS_DB || dbias == nullptr) return;
-  for (int i = threadIdx.x; i < k.c; i += kThreads) s_db[i] = 0.f;
-  __syncthreads();
+  if constexpr (HAS_DB) {
+    if (dbias == nullptr) return;
+    for (int i = threadIdx.x; i < k.c; i += kThreads) s_db[i] = 0.f;
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&s_db[v * 8 + j], db[j]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < k.c; i += kThreads) atomicAdd(dbias + i, s_db[i]);
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_db[v * 8 + j], db[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < k.c; i += kThreads) atomicAdd(dbias + i, s_db[i]);
+  }
 }
 
 // ================================================================================================
