@@ -12,3 +12,6 @@ cp /root/reference/run.py baseline/_ref/src/
 cp /root/reference/utils/*.py baseline/_ref/src/utils/
 ( cd /root/reference && sha256sum run.py utils/*.py ) > baseline/_ref/SHA256SUMS
 ( cd baseline/_ref/src && sha256sum -c ../SHA256SUMS ) | tail -3
+# real MNIST for the GPU-box training runs (gz IDX files, 11 MB; git-ignored like the rest of baseline/_ref)
+mkdir -p baseline/_ref/datasets/MNIST/raw
+cp /root/reference/datasets/MNIST/raw/*.gz baseline/_ref/datasets/MNIST/raw/

@@ -1,10 +1,13 @@
 """Gradient all-reduce bandwidth sweep (BASELINE.json config 5): fused NVLink kernel vs NCCL.
 
-    torchrun --nproc-per-node N benchmarks/allreduce_sweep.py [--out gpurun_out/allreduce_sweep_nN.json]
+    torchrun --nproc-per-node N benchmarks/allreduce_sweep.py [--out profiles/allreduce_sweep_nN.json]
 
-Buckets 64 KB - 256 MB fp32.  Device-timed (CUDA events), max over ranks, L2 flushed between iterations.
-bus GB/s = 2 (n-1)/n * bytes / time (the NCCL convention); the roofline is the measured 770 GB/s per
-direction per GPU (900 nominal)."""
+Buckets 64 KB - 256 MB of fp32 gradients.  Device-timed (CUDA events), max over ranks, L2 flushed between
+iterations.  Every fused number includes the 1/(world x loss_scale) multiply and the overflow scan; the bf16 rows
+also include the fp32 -> bf16 cast on send and the expansion back into the fp32 arena (the bucket is the same
+number of gradients, the wire carries half the bytes).  bus GB/s = 2 (n-1)/n x fp32 bytes / time (the NCCL
+convention, so bf16-wire rows can exceed the link rate); the roofline is the measured 770 GB/s per direction per
+GPU (900 nominal)."""
 import argparse, json, os, sys
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--max_mb", type=int, default=256)
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -22,11 +26,12 @@ def main():
     from ddpt_b200.ops import require_native
     from ddpt_b200.parallel.symm import SymmetricRegion
     ext = require_native()
-    max_elems = 256 * 1024 * 1024 // 4
+    max_elems = a.max_mb * 1024 * 1024 // 4
     region = SymmetricRegion(max_elems, dev)
     state = torch.tensor([1.0, 1.0, 0.0, 0.0, 0.0], device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     nccl_buf = torch.randn(max_elems, device=dev)
+    nccl_bf16 = nccl_buf.bfloat16()
     region.tensor.copy_(nccl_buf)
 
     def timed(fn, iters):
@@ -44,30 +49,39 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def fused(n, algo, wire, blocks):
+        return lambda: ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, region.scratch_ptrs,
+                                           region.mc_scratch_ptr, rank, 0, n, state, state[2:3], 0, algo, wire, blocks,
+                                           20000)
+
     rows = []
     size = 64 * 1024
-    while size <= 256 * 1024 * 1024:
+    while size <= a.max_mb * 1024 * 1024:
         n = size // 4
         row = {"bytes": size}
-        algos = {"auto": 0, "twoshot": 2}
-        if n <= 64 * 1024:
-            algos["oneshot"] = 1
-        if region.mc_ptr:
-            algos["multimem"] = 3
-        for name, algo in algos.items():
-            ms = timed(lambda: ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, rank, 0, n,
-                                                   state, state[2:3], 0, algo, 0, 20000), a.iters)
-            row[f"fused_{name}_us"] = ms * 1e3
-            row[f"fused_{name}_busGBs"] = 2 * (world - 1) / world * size / (ms * 1e-3) / 1e9
+        variants = {"f32_auto": (0, 0, 0), "bf16_auto": (0, 1, 0), "f32_twoshot_p2p": (2, 0, 0),
+                    "bf16_twoshot_p2p": (2, 1, 0)}
+        if size >= 4 * 1024 * 1024:
+            variants["f32_auto_b64"] = (0, 0, 64)
+            variants["bf16_auto_b64"] = (0, 1, 64)
+            variants["bf16_auto_b16"] = (0, 1, 16)
+        for name, (algo, wire, blocks) in variants.items():
+            ms = timed(fused(n, algo, wire, blocks), a.iters)
+            row[f"fused_{name}_us"] = round(ms * 1e3, 2)
+            row[f"fused_{name}_busGBs"] = round(2 * (world - 1) / world * size / (ms * 1e-3) / 1e9, 1)
         view = nccl_buf[:n]
         ms = timed(lambda: dist.all_reduce(view), a.iters)
-        row["nccl_us"] = ms * 1e3
-        row["nccl_busGBs"] = 2 * (world - 1) / world * size / (ms * 1e-3) / 1e9
+        row["nccl_us"] = round(ms * 1e3, 2)
+        row["nccl_busGBs"] = round(2 * (world - 1) / world * size / (ms * 1e-3) / 1e9, 1)
+        v16 = nccl_bf16[:n]
+        ms = timed(lambda: dist.all_reduce(v16), a.iters)
+        row["nccl_bf16_us"] = round(ms * 1e3, 2)          # same gradient count sent as bf16 (no cast / scale / check)
         rows.append(row)
         size *= 4
     if rank == 0:
         out = {"world": world, "provider": region.provider, "multicast": bool(region.mc_ptr), "rows": rows,
-               "link_GBs_measured_per_direction": 770, "link_GBs_nominal": 900}
+               "link_GBs_measured_per_direction": 770, "link_GBs_nominal": 900,
+               "note": "auto = one-shot push <= 256 KiB, else multimem two-shot when multicast is mapped"}
         print(json.dumps(out, indent=1))
         if a.out:
             os.makedirs(os.path.dirname(a.out), exist_ok=True)

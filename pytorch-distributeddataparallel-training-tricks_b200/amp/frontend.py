@@ -47,8 +47,27 @@ class AmpState:
     scaler: Optional[LossScaler] = None
     optimizers: List[Any] = field(default_factory=list)
     models: List[torch.nn.Module] = field(default_factory=list)
-    reducers: List[Any] = field(default_factory=list)   # DDP reducers that fuse the unscale
+    _reducers: List[Any] = field(default_factory=list)  # (weakref(reducer), weakref(module)) of live DDP wrappers
     enabled: bool = False
+
+    def register_reducer(self, reducer, module=None) -> None:
+        """A DDP wrapper announces its reducer.  Re-wrapping the same module replaces the old entry and dead
+        wrappers drop out, so a stale reducer can never veto ``fused_by_reducer`` (which would unscale twice)."""
+        import weakref
+        mref = weakref.ref(module) if module is not None else None
+        keep = []
+        for rref, mr in self._reducers:
+            if rref() is None or (mref is not None and mr is not None and mr() is module):
+                continue
+            keep.append((rref, mr))
+        keep.append((weakref.ref(reducer), mref))
+        self._reducers = keep
+
+    @property
+    def reducers(self) -> List[Any]:
+        live = [(r, m) for r, m in self._reducers if r() is not None]
+        self._reducers = live
+        return [r() for r, _ in live]
 
 
 _STATE = AmpState()
@@ -145,12 +164,13 @@ def scale_loss(loss: torch.Tensor, optimizers, loss_id: int = 0, delay_unscale: 
         return
     scaler = st.scaler
     scaler.begin_step()
-    for r in st.reducers:
+    reducers = st.reducers
+    for r in reducers:
         r.expect_scaled_grads(scaler)
     yield scaler.scale(loss)
     if delay_unscale:
         return
-    fused_by_reducer = bool(st.reducers) and all(r.consumed_scaler() for r in st.reducers)
+    fused_by_reducer = bool(reducers) and all(r.consumed_scaler() for r in reducers)
     for opt in opt_list:
         fused_opt = getattr(getattr(opt, "optimizer", opt), "_fused", None)
         if fused_opt is not None:

@@ -46,6 +46,8 @@ def build_parser() -> argparse.ArgumentParser:
                      help="mixed precision level: O0 fp32, O1 bf16, O1-fp16, O1-fp8 (block scaled)")
     ext.add_argument("--comm", default="auto", choices=("auto", "fused", "pg"),
                      help="gradient all-reduce: fused NVLink kernel or process-group collective")
+    ext.add_argument("--comm_wire", default="fp32", choices=("fp32", "bf16"),
+                     help="wire format of the fused all-reduce: fp32, or bf16 (cast fused into the send, fp32 accumulate)")
     ext.add_argument("--bucket_cap_mb", default=25.0, type=float, help="gradient bucket size")
     ext.add_argument("--arch", default="toy_net", choices=("toy_net", "resnet50"),
                      help="model family")

@@ -16,17 +16,22 @@ void cuda_ok(cudaError_t e, const char* what) {
 }
 
 ddpt::AllReduceArgs make_args(const std::vector<int64_t>& peer_ptrs, const std::vector<int64_t>& signal_ptrs,
-                              int64_t mc_ptr, int64_t rank, int64_t offset, int64_t numel,
+                              int64_t mc_ptr, const std::vector<int64_t>& scratch_ptrs, int64_t mc_scratch_ptr,
+                              int64_t rank, int64_t offset, int64_t numel,
                               const c10::optional<at::Tensor>& scaler_state, const c10::optional<at::Tensor>& found_inf,
-                              int64_t channel, int64_t algo, int64_t blocks, int64_t timeout_ms = 0) {
+                              int64_t channel, int64_t algo, int64_t wire, int64_t blocks, int64_t timeout_ms = 0) {
   const int world = (int)peer_ptrs.size();
   TORCH_CHECK(world >= 1 && world <= ddpt::kMaxRanks && signal_ptrs.size() == peer_ptrs.size());
+  TORCH_CHECK(scratch_ptrs.empty() || scratch_ptrs.size() == peer_ptrs.size(), "one scratch pointer per rank (or none)");
+  TORCH_CHECK(rank >= 0 && rank < world, "bad rank");
   ddpt::AllReduceArgs a{};
   for (int r = 0; r < world; ++r) {
     a.peer_bufs[r] = reinterpret_cast<float*>(peer_ptrs[r]);
     a.peer_signals[r] = reinterpret_cast<uint32_t*>(signal_ptrs[r]);
+    a.peer_scratch[r] = scratch_ptrs.empty() ? nullptr : reinterpret_cast<unsigned char*>(scratch_ptrs[r]);
   }
   a.mc_buf = reinterpret_cast<float*>(mc_ptr);
+  a.mc_scratch = reinterpret_cast<unsigned char*>(mc_scratch_ptr);
   a.rank = (int)rank; a.world = world; a.offset = offset; a.numel = numel;
   if (scaler_state.has_value()) {
     TORCH_CHECK(scaler_state->is_cuda() && scaler_state->scalar_type() == at::kFloat && scaler_state->numel() >= 5);
@@ -36,25 +41,30 @@ ddpt::AllReduceArgs make_args(const std::vector<int64_t>& peer_ptrs, const std::
     TORCH_CHECK(found_inf->is_cuda() && found_inf->scalar_type() == at::kFloat);
     a.found_inf = found_inf->data_ptr<float>();
   }
-  a.channel = (int)channel; a.algo = (int)algo; a.blocks = (int)blocks; a.timeout_ms = (int)timeout_ms;
+  a.channel = (int)channel; a.algo = (int)algo; a.wire = (int)wire; a.blocks = (int)blocks; a.timeout_ms = (int)timeout_ms;
   return a;
 }
 
-void fused_allreduce(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t mc_ptr, int64_t rank,
+void fused_allreduce(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t mc_ptr,
+                     std::vector<int64_t> scratch_ptrs, int64_t mc_scratch_ptr, int64_t rank,
                      int64_t offset, int64_t numel, c10::optional<at::Tensor> scaler_state,
-                     c10::optional<at::Tensor> found_inf, int64_t channel, int64_t algo, int64_t blocks,
+                     c10::optional<at::Tensor> found_inf, int64_t channel, int64_t algo, int64_t wire, int64_t blocks,
                      int64_t timeout_ms) {
-  ddpt::launch_fused_allreduce(make_args(peer_ptrs, signal_ptrs, mc_ptr, rank, offset, numel, scaler_state, found_inf,
-                                         channel, algo, blocks, timeout_ms), cur());
+  ddpt::launch_fused_allreduce(make_args(peer_ptrs, signal_ptrs, mc_ptr, scratch_ptrs, mc_scratch_ptr, rank, offset,
+                                         numel, scaler_state, found_inf, channel, algo, wire, blocks, timeout_ms), cur());
 }
 
-void symm_broadcast(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t rank, int64_t root,
-                    int64_t offset, int64_t numel, int64_t channel) {
-  ddpt::launch_symm_broadcast(make_args(peer_ptrs, signal_ptrs, 0, rank, offset, numel, c10::nullopt, c10::nullopt,
-                                        channel, 0, 0), (int)root, cur());
+// root's [offset, offset + numel) floats of a symmetric region replace every rank's copy (one launch)
+void symm_broadcast(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t mc_ptr, int64_t rank,
+                    int64_t root, int64_t offset, int64_t numel, int64_t channel, int64_t timeout_ms) {
+  ddpt::launch_symm_broadcast(make_args(peer_ptrs, signal_ptrs, mc_ptr, {}, 0, rank, offset, numel, c10::nullopt,
+                                        c10::nullopt, channel, 0, 0, 0, timeout_ms), (int)root, cur());
 }
 
 int64_t signal_pad_bytes() { return (int64_t)ddpt::kSignalWords * 4; }
+// bytes of the scratch region for an arena of `stage_elems` elements: push slots + 16-bit staging
+int64_t scratch_bytes(int64_t stage_elems) { return (int64_t)ddpt::kPushBytes + 2 * ((stage_elems + 127) / 128 * 128); }
+int64_t oneshot_max_elems() { return (int64_t)ddpt::kOneShotMaxElems; }
 
 // ---- CUDA IPC symmetric allocation (fallback) -----------------------------------------------------------
 // Returns (device pointer, 64-byte IPC handle).  Memory comes from cudaMalloc (not the caching allocator)
@@ -102,9 +112,14 @@ at::Tensor tensor_from_ptr(int64_t ptr, int64_t numel, int64_t device, bool is_u
 
 void ddpt_bind_comm(pybind11::module_& m) {
   m.def("fused_allreduce", &fused_allreduce, py::arg("peer_ptrs"), py::arg("signal_ptrs"), py::arg("mc_ptr"),
-        py::arg("rank"), py::arg("offset"), py::arg("numel"), py::arg("scaler_state"), py::arg("found_inf"),
-        py::arg("channel"), py::arg("algo"), py::arg("blocks"), py::arg("timeout_ms") = 0);
-  m.def("symm_broadcast", &symm_broadcast);
+        py::arg("scratch_ptrs"), py::arg("mc_scratch_ptr"), py::arg("rank"), py::arg("offset"), py::arg("numel"),
+        py::arg("scaler_state"), py::arg("found_inf"), py::arg("channel"), py::arg("algo"), py::arg("wire") = 0,
+        py::arg("blocks") = 0, py::arg("timeout_ms") = 0);
+  m.def("symm_broadcast", &symm_broadcast, py::arg("peer_ptrs"), py::arg("signal_ptrs"), py::arg("mc_ptr"),
+        py::arg("rank"), py::arg("root"), py::arg("offset"), py::arg("numel"), py::arg("channel"),
+        py::arg("timeout_ms") = 0);
+  m.def("scratch_bytes", &scratch_bytes);
+  m.def("oneshot_max_elems", &oneshot_max_elems);
   m.def("signal_pad_bytes", &signal_pad_bytes);
   m.def("ipc_alloc", &ipc_alloc);
   m.def("ipc_open", &ipc_open);

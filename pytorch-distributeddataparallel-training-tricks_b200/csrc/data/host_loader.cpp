@@ -48,13 +48,16 @@ class PinnedGatherLoader {
     for (auto& w : workers_) w.join();
   }
 
-  // Begin an epoch: `indices` is copied; batches are [b*batch, min((b+1)*batch, n)).
-  void start_epoch(std::vector<int64_t> indices, int64_t num_batches) {
+  // Begin an epoch: `n` int64 sample indices at `indices_ptr` are copied (no Python list, GIL released while the
+  // previous epoch drains); batches are [b*batch, min((b+1)*batch, n)).
+  void start_epoch(uintptr_t indices_ptr, int64_t n, int64_t num_batches) {
+    const int64_t* src = reinterpret_cast<const int64_t*>(indices_ptr);
+    for (int64_t i = 0; i < n; ++i)
+      if (src[i] < 0 || src[i] >= num_rows_) throw std::out_of_range("sample index out of range");
+    py::gil_scoped_release nogil;
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [this] { return active_workers_ == 0; });       // previous epoch fully drained
-    for (auto idx : indices)
-      if (idx < 0 || idx >= num_rows_) throw std::out_of_range("sample index out of range");
-    indices_ = std::move(indices);
+    indices_.assign(src, src + n);
     num_batches_ = num_batches;
     for (auto& s : slots_) { s.batch = -1; s.ready = false; s.free = true; }
     next_consume_ = 0;

@@ -53,7 +53,57 @@ struct KernelArgs {
   int relu, out_fp32, a_rows_bytes;
   int stages;                   // pipeline depth (stage = kbs K blocks of A [+ B unless resident])
   int kbs;                      // K blocks (tap x 64-channel chunk) per pipeline stage: amortises the barrier round trip
+  int a_w, a_h;                 // extent of the activation tensor (taps whose whole brick is out of range are skipped)
+  int pair_interleave;          // CTA pair: the two row tiles of a unit are the same pixel brick of adjacent image groups
 };
+
+// Row tile -> brick coordinates.  Default order: brick column fastest, then brick row, then image group.  With
+// pair_interleave the two tiles of a CTA pair (tile_m = 2q, 2q+1) share the pixel position and take adjacent image
+// groups, so both need exactly the same filter taps (data gradient: border positions skip out-of-range taps).
+__device__ __forceinline__ void decode_tile(const KernelArgs& a, int tile_m, int& tw, int& th, int& tn) {
+  const int positions = a.tiles_w * a.tiles_h;
+  int pos;
+  if (a.pair_interleave) {
+    const int q = tile_m >> 1;
+    pos = q % positions;
+    tn = (q / positions) * 2 + (tile_m & 1);
+  } else {
+    pos = tile_m % positions;
+    tn = tile_m / positions;
+  }
+  tw = pos % a.tiles_w;
+  th = pos / a.tiles_w;
+}
+
+// Filter taps whose shifted brick intersects the activation tensor at all: [lo, hi] along one axis.  For the forward
+// ('valid') convolution every tap qualifies; for the data gradient a brick at the border of the input image only
+// sees part of the filter -- with one-pixel bricks (128 images x 1 x 1) the MMA count drops from taps x pixels to the
+// nominal sum over pixels of the taps that actually reach them (Toy_Net conv.10: 576 instead of 900 per image group).
+__device__ __forceinline__ void tap_range(int origin, int box, int extent, int taps, int sign, int& lo, int& hi) {
+  lo = taps; hi = -1;
+  for (int t = 0; t < taps; ++t) {
+    const int start = origin + sign * t;
+    if (start + box > 0 && start < extent) { lo = min(lo, t); hi = max(hi, t); }
+  }
+  if (hi < 0) { lo = 0; hi = 0; }            // nothing in range (padding tile): one tap of zeros defines the accumulator
+}
+
+struct TileTaps { int tx0, tx1, ty0, ty1; };
+// Union over the MC row tiles of a work unit (the leader issues one MMA stream for both CTAs).
+template <int MC>
+__device__ __forceinline__ TileTaps unit_taps(const KernelArgs& a, int tile_m0) {
+  TileTaps r{a.taps_w, -1, a.num_taps / a.taps_w, -1};
+#pragma unroll
+  for (int i = 0; i < MC; ++i) {
+    int tw, th, tn, lo, hi;
+    decode_tile(a, tile_m0 + i, tw, th, tn);
+    tap_range(tw * a.box_w + a.a_w_off, a.box_w, a.a_w, a.taps_w, a.tap_sign, lo, hi);
+    r.tx0 = min(r.tx0, lo); r.tx1 = max(r.tx1, hi);
+    tap_range(th * a.box_h + a.a_h_off, a.box_h, a.a_h, a.num_taps / a.taps_w, a.tap_sign, lo, hi);
+    r.ty0 = min(r.ty0, lo); r.ty1 = max(r.ty1, hi);
+  }
+  return r;
+}
 
 
 // B_RES: the whole weight matrix (all taps x channel chunks of the single column block) is loaded into shared
@@ -88,7 +138,6 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   constexpr uint16_t kMask = (1u << MC) - 1;
   const int total_kb = args.num_taps * args.k_chunks;
   const int kStages = args.stages, kbs = args.kbs;
-  const int steps_per_tile = (total_kb + kbs - 1) / kbs;   // pipeline steps (barrier round trips) per tile
   const int a_stage_bytes = kbs * kAStageBytes;
   const int b_stage_bytes = kbs * kBStageBytes;
 
@@ -149,9 +198,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       uint32_t ring_phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
         const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
-        const int tw = tile_m % args.tiles_w;
-        const int th = (tile_m / args.tiles_w) % args.tiles_h;
-        const int tn = tile_m / (args.tiles_w * args.tiles_h);
+        int tw, th, tn;
+        decode_tile(args, tile_m, tw, th, tn);
+        const TileTaps taps = unit_taps<MC>(args, (unit / num_n_tiles) * MC);
+        const int ntx = taps.tx1 - taps.tx0 + 1;
+        const int tile_kb = ntx * (taps.ty1 - taps.ty0 + 1) * args.k_chunks;     // K blocks of this tile
+        const int steps_per_tile = (tile_kb + kbs - 1) / kbs;
         // A-box origin of tap (0, 0) and the weight column of this CTA; the (tap, channel chunk) of each K block is
         // advanced with counters.  ncu on the first version (profiles/ncu_fwd10_pair_v1.txt): the elected producer
         // lane spent ~85 % of its samples in two runtime integer divisions per K block (I2F / MUFU.RCP chains on one
@@ -159,13 +211,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         // capped every variant of this kernel at 70 % tensor-pipe activity.
         const int wb = tw * args.box_w + args.a_w_off, hb = th * args.box_h + args.a_h_off, n0 = tn * args.box_n;
         const int col0 = tile_n * BN + (MC > 1 ? rank * (BN / MC) : 0);
-        int kb = 0, chunk = 0, sx = 0, dh = 0, tap_col = col0;   // tap_col: B_MN column of this tap = tap * n_total + col0
+        int kb = 0, chunk = 0, tx = taps.tx0;
+        int sx = args.tap_sign * taps.tx0, dh = args.tap_sign * taps.ty0;
+        int tap = taps.ty0 * args.taps_w + taps.tx0;            // weight tap index: B K-offset tap*C, B_MN column tap*n_total
         for (int step = 0; step < steps_per_tile; ++step) {
           const int s = ring_s;
           const uint32_t phase = ring_phase;
           if (++ring_s == kStages) { ring_s = 0; ring_phase ^= 1; }
           mbar_wait(&empty_bar[s], phase ^ 1, 1);
-          const int nkb = min(kbs, total_kb - kb);
+          const int nkb = min(kbs, tile_kb - kb);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nkb) * MC * tx_bytes);
           uint8_t* a_dst = smem_a + s * a_stage_bytes;
           uint8_t* b_dst = smem_b + s * b_stage_bytes;
@@ -175,9 +229,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             if (B_RES) {
               // weights are resident
             } else if (!B_MN) {
-              if (MC > 1) tma_load_2d_pair(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
-              else tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * kBlockK, col0);
+              const int kcol = (tap * args.k_chunks + chunk) * kBlockK;
+              if (MC > 1) tma_load_2d_pair(b_dst, &tmap_b, &full_bar[s], kcol, col0);
+              else tma_load_2d(b_dst, &tmap_b, &full_bar[s], kcol, col0);
             } else {
+              const int tap_col = tap * args.n_total + col0;
 #pragma unroll
               for (int jj = 0; jj < BN / 64 / MC; ++jj) {
                 if (MC > 1) tma_load_2d_pair(b_dst + jj * (kBlockK * 128), &tmap_b, &full_bar[s], tap_col + jj * 64, chunk * kBlockK);
@@ -185,11 +241,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
               }
             }
             ++kb;
-            if (++chunk == args.k_chunks) {                 // next filter tap: one column right, or next row
+            if (++chunk == args.k_chunks) {                 // next filter tap: one column over, or next filter row
               chunk = 0;
-              tap_col += args.n_total;
+              ++tap;
               sx += args.tap_sign;
-              if (sx == args.tap_sign * args.taps_w) { sx = 0; dh += args.tap_sign; }
+              if (++tx > taps.tx1) {
+                tx = taps.tx0;
+                sx = args.tap_sign * taps.tx0;
+                dh += args.tap_sign;
+                tap += args.taps_w - ntx;
+              }
             }
           }
         }
@@ -206,18 +267,30 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const TileTaps taps = unit_taps<MC>(args, (unit / num_n_tiles) * MC);
+        const int ntx = taps.tx1 - taps.tx0 + 1;
+        const int tile_kb = ntx * (taps.ty1 - taps.ty0 + 1) * args.k_chunks;
+        const int steps_per_tile = (tile_kb + kbs - 1) / kbs;
+        int chunk = 0, tx = taps.tx0, tap = taps.ty0 * args.taps_w + taps.tx0;   // resident weights: tile index of the K block
         for (int step = 0; step < steps_per_tile; ++step) {
           const int s = ring_s;
           const uint32_t phase = ring_phase;
           if (++ring_s == kStages) { ring_s = 0; ring_phase ^= 1; }
           mbar_wait(&full_bar[s], phase, 2);
           tc_fence_after();
-          const int kb0 = step * kbs, nkb = min(kbs, total_kb - kb0);
+          const int kb0 = step * kbs, nkb = min(kbs, tile_kb - kb0);
           for (int j = 0; j < nkb; ++j) {
             const int kb = kb0 + j;
             const uint32_t a_addr = smem_u32(smem_a + s * a_stage_bytes + j * kAStageBytes);
-            const uint32_t b_addr = B_RES ? smem_u32(smem_b + kb * kBStageBytes)
+            const uint32_t b_addr = B_RES ? smem_u32(smem_b + (tap * args.k_chunks + chunk) * kBStageBytes)
                                           : smem_u32(smem_b + s * b_stage_bytes + j * kBStageBytes);
+            if (B_RES) {
+              if (++chunk == args.k_chunks) {
+                chunk = 0;
+                ++tap;
+                if (++tx > taps.tx1) { tx = taps.tx0; tap += args.taps_w - ntx; }
+              }
+            }
             const uint64_t adesc0 = make_smem_desc(a_addr, 0, 1024);
             const uint64_t bdesc0 = B_MN ? make_smem_desc(b_addr, kBlockK * 128, 1024) : make_smem_desc(b_addr, 0, 1024);
 #pragma unroll
@@ -250,9 +323,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     uint32_t t = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++t) {
       const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
-      const int tw = tile_m % args.tiles_w;
-      const int th = (tile_m / args.tiles_w) % args.tiles_h;
-      const int tn = tile_m / (args.tiles_w * args.tiles_h);
+      int tw, th, tn;
+      decode_tile(args, tile_m, tw, th, tn);
       const int n = tn * args.box_n + dn, h = th * args.box_h + dh, w = tw * args.box_w + dw;
       const bool valid = dn < args.box_n && n < args.out_n && h < args.out_h && w < args.out_w;
       const long long out_row = (static_cast<long long>(n) * args.out_h + h) * args.out_w + w;
@@ -385,6 +457,8 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
   a.stat_partials = p.stat_partials; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
+  a.a_w = p.a_w; a.a_h = p.a_h;
+  a.pair_interleave = (MC == 2 && tiles_n % 2 == 0 && p.taps_h * p.taps_w > 1) ? 1 : 0;
 
   if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)
     throw std::runtime_error("conv_gemm: unsupported shape (C % 64, N % BLOCK_N, brick <= 128 rows)");

@@ -86,20 +86,26 @@ class NativeReducer : public std::enable_shared_from_this<NativeReducer> {
     fused_ = false;
   }
 
-  void use_fused(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t mc_ptr, int64_t rank,
-                 int64_t algo, at::Tensor unit_state) {
+  void use_fused(std::vector<int64_t> peer_ptrs, std::vector<int64_t> signal_ptrs, int64_t mc_ptr,
+                 std::vector<int64_t> scratch_ptrs, int64_t mc_scratch_ptr, int64_t rank, int64_t algo, int64_t wire,
+                 int64_t blocks, at::Tensor unit_state) {
     world_ = (int)peer_ptrs.size();
     TORCH_CHECK(world_ >= 1 && world_ <= ddpt::kMaxRanks && signal_ptrs.size() == peer_ptrs.size());
+    TORCH_CHECK(scratch_ptrs.empty() || scratch_ptrs.size() == peer_ptrs.size());
     TORCH_CHECK(arena_.is_cuda(), "fused back end needs a CUDA arena");
     base_ = ddpt::AllReduceArgs{};
     for (int r = 0; r < world_; ++r) {
       base_.peer_bufs[r] = reinterpret_cast<float*>(peer_ptrs[r]);
       base_.peer_signals[r] = reinterpret_cast<uint32_t*>(signal_ptrs[r]);
+      base_.peer_scratch[r] = scratch_ptrs.empty() ? nullptr : reinterpret_cast<unsigned char*>(scratch_ptrs[r]);
     }
     base_.mc_buf = reinterpret_cast<float*>(mc_ptr);
+    base_.mc_scratch = reinterpret_cast<unsigned char*>(mc_scratch_ptr);
     base_.rank = (int)rank;
     base_.world = world_;
     base_.algo = (int)algo;
+    base_.wire = (int)wire;
+    base_.blocks = (int)blocks;
     unit_state_ = std::move(unit_state);
     comm_stream_ = c10::cuda::getStreamFromPool(/*isHighPriority=*/true, arena_.device().index());
     fused_ = true;
@@ -171,7 +177,7 @@ class NativeReducer : public std::enable_shared_from_this<NativeReducer> {
       ddpt::AllReduceArgs a = base_;
       a.offset = spec.start;
       a.numel = spec.numel;
-      a.channel = b % ddpt::kCommChannels;
+      a.channel = b % (ddpt::kCommChannels - 1);          // the last channel is the buffer broadcast's
       at::Tensor state = scaler_state_.has_value() ? *scaler_state_ : unit_state_;
       a.scaler_state = state.data_ptr<float>();
       a.found_inf = state.data_ptr<float>() + 2;

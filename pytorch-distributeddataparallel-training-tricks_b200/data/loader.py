@@ -48,8 +48,10 @@ class BatchLoader:
             from ..ops import host_loader
             self._native = host_loader.PinnedGatherLoader(data.images, data.labels, self.batch_size,
                                                           self.device)
-        # host-visible byte counters (bench.py reports them)
+        # host-visible counters (bench.py reports them)
         self.h2d_bytes = 0
+        self.samples_yielded = 0
+        self.quiet = False          # True: iterate_loader shows no progress bar
 
     # -- sizing -----------------------------------------------------------
     def _num_samples(self) -> int:
@@ -72,10 +74,12 @@ class BatchLoader:
             for b in range(nb):
                 sel = idx_dev[b * self.batch_size:(b + 1) * self.batch_size]
                 img = self._dev_images.index_select(0, sel)
+                self.samples_yielded += int(sel.numel())
                 yield (img.float().div_(255.0) if self.as_float else img), self._dev_labels.index_select(0, sel)
         elif self.mode == "pinned":
             for img, tgt, nbytes in self._native.epoch(idx, nb):
                 self.h2d_bytes += nbytes
+                self.samples_yielded += int(tgt.numel())
                 yield (img.float().div_(255.0) if self.as_float else img), tgt
         else:
             images, labels = self.data.images, self.data.labels
@@ -83,6 +87,7 @@ class BatchLoader:
                 sel = idx[b * self.batch_size:(b + 1) * self.batch_size]
                 img = images.index_select(0, sel).view(-1, 1, 28, 28)
                 tgt = labels.index_select(0, sel)
+                self.samples_yielded += int(sel.numel())
                 if self.device.type == "cuda":
                     img = img.pin_memory().to(self.device, non_blocking=True)
                     tgt = tgt.pin_memory().to(self.device, non_blocking=True)

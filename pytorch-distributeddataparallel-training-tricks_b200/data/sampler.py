@@ -30,6 +30,8 @@ class ShardedSampler:
         self.num_replicas, self.rank = int(num_replicas), int(rank)
         self.shuffle, self.seed, self.drop_last = shuffle, seed, drop_last
         self.epoch = 0
+        self._cache = {}            # epoch -> indices; filled one epoch ahead by a background thread
+        self._prefetch = None
         if drop_last and self.dataset_len % self.num_replicas:
             self.num_samples = math.ceil((self.dataset_len - self.num_replicas) / self.num_replicas)
         else:
@@ -40,10 +42,31 @@ class ShardedSampler:
         self.epoch = int(epoch)
 
     def indices(self) -> torch.Tensor:
-        """This rank's sample indices for the current epoch (int64, CPU)."""
+        """This rank's sample indices for the current epoch (int64, CPU).  The next epoch's permutation is
+        computed on a background thread while this epoch trains (``randperm`` releases the GIL), so the host
+        never stalls the device at an epoch boundary."""
+        import threading
+        if self._prefetch is not None:
+            self._prefetch.join()
+            self._prefetch = None
+        cur = self._cache.pop(self.epoch, None)
+        if cur is None:
+            cur = self._indices_for(self.epoch)
+        self._cache.clear()
+        nxt = self.epoch + 1
+
+        def work():
+            self._cache[nxt] = self._indices_for(nxt)
+
+        if self.shuffle:
+            self._prefetch = threading.Thread(target=work, daemon=True)
+            self._prefetch.start()
+        return cur
+
+    def _indices_for(self, epoch: int) -> torch.Tensor:
         if self.shuffle:
             g = torch.Generator()
-            g.manual_seed(self.seed + self.epoch)
+            g.manual_seed(self.seed + epoch)
             order = torch.randperm(self.dataset_len, generator=g)
         else:
             order = torch.arange(self.dataset_len)

@@ -89,7 +89,8 @@ def train(args) -> dict:
         parallel_model = DistributedDataParallel(
             model, device_ids=[args.local_rank] if device.type == "cuda" else None,
             output_device=args.local_rank if device.type == "cuda" else None,
-            bucket_cap_mb=getattr(args, "bucket_cap_mb", 25.0), comm=getattr(args, "comm", "auto"))
+            bucket_cap_mb=getattr(args, "bucket_cap_mb", 25.0), comm=getattr(args, "comm", "auto"),
+            comm_wire=getattr(args, "comm_wire", "fp32"))
     else:
         parallel_model = model
     if device.type == "cuda":

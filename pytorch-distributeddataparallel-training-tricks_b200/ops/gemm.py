@@ -43,6 +43,35 @@ def pick_box(out_n: int, out_h: int, out_w: int, multiple_of: int = 1, max_rows:
     return best
 
 
+def _axis_taps(out_len: int, box: int, taps: int) -> int:
+    """Sum over the bricks along one axis of the filter taps whose shifted brick still overlaps the (out_len - taps + 1)
+    long gradient tensor -- the data-gradient kernel skips the others (csrc/nn/conv_gemm_persistent.cu: tap_range)."""
+    src = out_len - taps + 1
+    total = 0
+    for t0 in range(0, out_len, box):
+        total += max(1, sum(1 for t in range(taps) if t0 - t + box > 0 and t0 - t < src))
+    return total
+
+
+@functools.lru_cache(maxsize=None)
+def pick_box_dgrad(out_n: int, out_h: int, out_w: int, kh: int, kw: int) -> Tuple[int, int, int]:
+    """Brick for the data gradient of a 'valid' convolution: the one with the fewest (128-row tile x filter tap) MMA
+    groups once out-of-range taps are skipped.  Small images favour one-pixel bricks over many images
+    (bn x 1 x 1): Toy_Net conv.10 (10x10 <- 8x8) needs 576 tile-taps per 128 images instead of 1152."""
+    best, best_key = None, None
+    sizes = lambda n: sorted({1, 2, 4, 8, 16, 32, 64, 128, n} & set(range(1, n + 1)))
+    for bw in sizes(out_w):
+        for bh in sizes(out_h):
+            if bw * bh > 128:
+                continue
+            bn = min(out_n, 128 // (bw * bh))
+            cost = -(-out_n // bn) * _axis_taps(out_h, bh, kh) * _axis_taps(out_w, bw, kw)
+            key = (-cost, bw, bh)
+            if best_key is None or key > best_key:
+                best, best_key = (bn, bh, bw), key
+    return best
+
+
 def use_persistent(flag: Optional[bool] = None) -> bool:
     """Persistent (one CTA per SM, double-buffered TMEM) GEMM kernels; DDPT_GEMM_PERSISTENT=0 disables."""
     if flag is not None:
@@ -156,6 +185,8 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
     bn = _block_n(c_in, block_n)
     mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, pair)
+    if mode in (1, 3) and kh * kw > 1 and os.environ.get("DDPT_DGRAD_SKIP_TAPS", "1") != "0":
+        box = pick_box_dgrad(n, h, w, kh, kw)       # the persistent kernels skip filter taps that miss the brick
     ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
                   None, False, None, 1, bn, mode)
     return out

@@ -40,7 +40,8 @@ class PinnedGatherLoader:
         self.image_shape = tuple(images.shape[1:])
 
     def epoch(self, indices: torch.Tensor, num_batches: int) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
-        self._native.start_epoch(indices.tolist(), int(num_batches))
+        idx = indices.to(torch.int64).contiguous()
+        self._native.start_epoch(idx.data_ptr(), idx.numel(), int(num_batches))
         pending = []            # (slot, event) whose H2D copy may still be in flight
         while True:
             slot, rows = self._native.next()

@@ -112,7 +112,9 @@ class StepEngine:
                     if self.wgrad_stream is not None:      # the bucket also holds gradients produced on the side stream
                         ev = torch.cuda.Event()
                         ev.record(self.wgrad_stream)
-                        self.comm_stream.wait_event(ev)
+                        # the stream that will issue the collective must see them: the comm stream for the fused
+                        # kernel, the main stream for process-group back ends (they ignore comm_stream)
+                        (self.comm_stream if getattr(backend, "uses_comm_stream", False) else main).wait_event(ev)
                     backend.launch_on(self.comm_stream, main, arena, b, scaler)
 
             fm.backward_impl(batch, grads, target=t, loss_scale=scaler.scale_tensor, on_ready=on_ready,

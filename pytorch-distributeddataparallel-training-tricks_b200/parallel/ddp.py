@@ -53,7 +53,8 @@ class DistributedDataParallel(nn.Module):
     def __init__(self, module: nn.Module, device_ids=None, output_device=None,
                  broadcast_buffers: bool = True, bucket_cap_mb: float = 25.0,
                  process_group=None, comm: str = "auto", find_unused_parameters: bool = False,
-                 gradient_as_bucket_view: bool = True):
+                 gradient_as_bucket_view: bool = True, comm_wire: str = "fp32",
+                 tail_bucket_kb: float = 256.0):
         super().__init__()
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("DistributedDataParallel needs an initialised process group")
@@ -73,13 +74,19 @@ class DistributedDataParallel(nn.Module):
         self._verify_shapes()
 
         # ---- comm back end ----------------------------------------------------------
+        # comm="fused": our NVLink kernels or an exception (never a silent NCCL fallback); "auto": fused when it
+        # works, else process-group collectives with a warning; "pg": torch.distributed (gloo / the NCCL baseline).
+        if comm not in ("auto", "fused", "pg"):
+            raise ValueError(f"comm must be 'auto', 'fused' or 'pg', not {comm!r}")
         backend = None
         grad_alloc = None
         self.comm = "pg"
+        if comm == "fused" and (self.device.type != "cuda" or self.world_size < 2):
+            raise RuntimeError("comm='fused' needs CUDA devices and world_size >= 2")
         if comm in ("auto", "fused") and self.device.type == "cuda" and self.world_size > 1:
             try:
                 from .symm import FusedNvlinkBackend
-                backend = FusedNvlinkBackend(self.device, process_group)
+                backend = FusedNvlinkBackend(self.device, process_group, wire=comm_wire)
                 grad_alloc = backend.allocate
                 self.comm = "fused"
             except Exception as exc:  # symmetric memory / extension unavailable
@@ -87,19 +94,33 @@ class DistributedDataParallel(nn.Module):
                     raise
                 import warnings
                 warnings.warn(f"fused NVLink all-reduce unavailable ({exc}); using process-group collectives")
-        if backend is None:
-            backend = ProcessGroupBackend(process_group)
+                backend = None
 
         # ---- arenas, buckets, initial sync, reducer ---------------------------------
-        self.buckets = plan_buckets(self._params, bucket_cap_mb)
-        self.arena = FlatArena(self._params, self.buckets, grad_allocator=grad_alloc)
+        self.buckets = plan_buckets(self._params, bucket_cap_mb, world_size=self.world_size,
+                                    tail_bucket_bytes=int(tail_bucket_kb * 1024))
+        try:
+            self.arena = FlatArena(self._params, self.buckets, grad_allocator=grad_alloc)
+        except Exception as exc:
+            if comm == "fused" or backend is None:
+                raise
+            import warnings
+            warnings.warn(f"fused NVLink all-reduce unavailable ({exc}); using process-group collectives")
+            backend, self.comm = None, "pg"
+            self.arena = FlatArena(self._params, self.buckets)
+        if backend is None:
+            backend = ProcessGroupBackend(process_group)
+        self.backend = backend
         if hasattr(backend, "bind"):
             backend.bind(self.arena)
+        self._buffer_floats = 0
+        if self.comm == "fused":
+            self._rehome_buffers(backend)
         self._sync_module_states()
         self.reducer = make_reducer(self.arena, backend, process_group)
         self._buffers_dirty = True  # mirrors torch's require_forward_param_sync
         from ..amp import current_state
-        current_state().reducers.append(self.reducer)
+        current_state().register_reducer(self.reducer, module)
         fused_opt_hook = getattr(module, "_ddpt_on_arena", None)
         if fused_opt_hook is not None:
             fused_opt_hook(self.arena)
@@ -113,12 +134,57 @@ class DistributedDataParallel(nn.Module):
             if other != mine:
                 raise RuntimeError(f"parameter shapes differ between rank {self.rank} and rank {r}")
 
-    def _sync_module_states(self) -> None:
+    def _rehome_buffers(self, backend) -> None:
+        """Move every buffer of the module (BatchNorm running statistics, step counters) into one symmetric
+        region so that rank 0's values reach all ranks with ONE launch of our broadcast kernel instead of one
+        NCCL broadcast per dtype.  Buffers keep their dtype/shape: each becomes a 16-byte aligned
+        view of the region."""
+        slots, seen, cursor = [], {}, 0
+        for mod in self.module.modules():
+            for name, buf in mod._buffers.items():
+                if buf is None or buf.device != self.device:
+                    continue
+                if id(buf) not in seen:
+                    seen[id(buf)] = cursor
+                    cursor += (buf.numel() * buf.element_size() + 15) // 16 * 16
+                slots.append((mod, name, buf, seen[id(buf)]))
+        if not slots:
+            return
+        self._buffer_floats = cursor // 4
+        region = backend.allocate_buffers(self._buffer_floats)
+        raw = region.view(torch.uint8)
+        views = {}
         with torch.no_grad():
-            dist.broadcast(self.arena.param_arena, src=0, group=self.process_group)
+            for mod, name, buf, off in slots:
+                if off not in views:
+                    nbytes = buf.numel() * buf.element_size()
+                    v = raw[off: off + nbytes].view(buf.dtype).view(buf.shape)
+                    v.copy_(buf)
+                    views[off] = v
+                mod._buffers[name] = views[off]
+
+    def _sync_module_states(self) -> None:
+        """Rank 0's parameters and buffers replace everyone's (reference: DDP constructor, utils/train.py:61)."""
+        with torch.no_grad():
+            if self.comm == "fused":
+                # the (symmetric, still empty) gradient arena is the staging: param -> grad arena on rank 0, our
+                # broadcast kernel, grad arena -> param arena everywhere.  No NCCL on this path.
+                be, arena = self.backend, self.arena
+                if self.rank == 0:
+                    arena.grad_arena.copy_(arena.param_arena)
+                r = be.region
+                be.ext.symm_broadcast(r.peer_ptrs, r.signal_ptrs, r.mc_ptr, r.rank, 0, 0, arena.numel, 7, 0)
+                arena.param_arena.copy_(arena.grad_arena)
+                arena.grad_arena.zero_()
+            else:
+                dist.broadcast(self.arena.param_arena, src=0, group=self.process_group)
         self._sync_buffers()
 
     def _sync_buffers(self) -> None:
+        if self.comm == "fused":
+            if self._buffer_floats:
+                self.backend.broadcast_buffers(self._buffer_floats, 0)
+            return
         bufs = [b for b in self.module.buffers()]
         if bufs:
             _flat_broadcast(bufs, 0, self.process_group)

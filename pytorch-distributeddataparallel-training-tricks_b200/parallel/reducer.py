@@ -50,6 +50,8 @@ class ProcessGroupBackend:
 
     # stream-explicit protocol used by the CUDA-graph step engine: the collective is issued synchronously on the
     # current (capturing) stream -- no overlap, but capturable and correct; this is the NCCL baseline path
+    uses_comm_stream = False             # the step engine makes the *main* stream wait for side-stream gradients
+
     def launch_on(self, comm_stream, main_stream, arena: FlatArena, bucket: Bucket, scaler=None) -> None:
         flat = arena.bucket_slice(bucket)
         flat.div_(self.world)
@@ -159,7 +161,8 @@ class NativeReducerAdapter:
                                          [b.start for b in self.buckets], [b.numel for b in self.buckets])
         if getattr(backend, "fuses_unscale", False):
             r = backend.region
-            self._native.use_fused(r.peer_ptrs, r.signal_ptrs, r.mc_ptr, r.rank, backend.algo, backend._unit)
+            self._native.use_fused(r.peer_ptrs, r.signal_ptrs, r.mc_ptr, r.scratch_ptrs, r.mc_scratch_ptr, r.rank,
+                                   backend.algo, backend.wire, backend.blocks, backend._unit)
         else:
             pg = process_group if process_group is not None else dist.distributed_c10d._get_default_group()
             self._native.use_process_group(pg)

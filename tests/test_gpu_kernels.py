@@ -14,7 +14,7 @@ def ext():
     return ops.require_native()
 
 
-@pytest.fixture(params=["halo", "persistent", "pair", "per_tile"], autouse=True)
+@pytest.fixture(params=["halo", "persistent", "pair", "per_tile"])
 def gemm_flavour(request, monkeypatch):
     """Every GEMM/conv test runs against all forward/dgrad kernels (halo reuse, persistent, persistent as CTA pairs
     with cta_group::2 MMAs, one CTA per tile)."""
@@ -38,7 +38,7 @@ def _rel_err(got, want):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k,bn", [(128, 64, 64, 64), (256, 128, 256, 128), (1024, 512, 8192, 128),
                                       (304, 256, 512, 256), (1000, 64, 128, 64)])
-def test_linear_fwd(ext, m, n, k, bn):
+def test_linear_fwd(ext, gemm_flavour, m, n, k, bn):
     from ddpt_b200.ops import gemm
     x, w = _bf16(m, k, seed=1), _bf16(n, k, scale=k ** -0.5, seed=2)
     bias = torch.randn(n, device="cuda")
@@ -49,7 +49,7 @@ def test_linear_fwd(ext, m, n, k, bn):
     assert _rel_err(yb, want.relu()) < 1e-2
 
 
-def test_linear_fwd_split_k(ext):
+def test_linear_fwd_split_k(ext, gemm_flavour):
     from ddpt_b200.ops import gemm
     x, w = _bf16(1024, 8192, seed=3), _bf16(512, 8192, scale=8192 ** -0.5, seed=4)
     y, _ = gemm.linear_fwd(x, w, None, out_dtype=torch.float32, split_k=4, block_n=128)
@@ -57,7 +57,7 @@ def test_linear_fwd_split_k(ext):
 
 
 @pytest.mark.parametrize("m,n,k", [(256, 128, 128), (1024, 8192, 512), (304, 512, 64)])
-def test_linear_dgrad_mn_major_b(ext, m, n, k):
+def test_linear_dgrad_mn_major_b(ext, gemm_flavour, m, n, k):
     """dx[M,K] = dy[M,N] @ w[N,K] -- B operand consumed MN-major."""
     from ddpt_b200.ops import gemm
     dy, w = _bf16(m, n, seed=5), _bf16(n, k, scale=n ** -0.5, seed=6)
@@ -66,7 +66,7 @@ def test_linear_dgrad_mn_major_b(ext, m, n, k):
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1024, 512, 8192), (304, 128, 256)])
-def test_linear_wgrad_mn_major_both(ext, m, n, k):
+def test_linear_wgrad_mn_major_both(ext, gemm_flavour, m, n, k):
     """dw[N,K] = dy[M,N]^T @ x[M,K] -- both operands MN-major, split-K reduction."""
     from ddpt_b200.ops import gemm
     dy, x = _bf16(m, n, seed=7), _bf16(m, k, seed=8)
@@ -86,7 +86,7 @@ def _conv_ref(x_nhwc, w_km, c_out, c_in):
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", CONVS)
-def test_conv3x3_fwd_and_stats(ext, n, h, w, ci, co):
+def test_conv3x3_fwd_and_stats(ext, gemm_flavour, n, h, w, ci, co):
     from ddpt_b200.ops import gemm
     x, wk = _bf16(n, h, w, ci, seed=9), _bf16(co, 9 * ci, scale=(9 * ci) ** -0.5, seed=10)
     bias = torch.randn(co, device="cuda")
@@ -105,7 +105,7 @@ def test_conv3x3_fwd_and_stats(ext, n, h, w, ci, co):
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", CONVS)
-def test_conv3x3_dgrad(ext, n, h, w, ci, co):
+def test_conv3x3_dgrad(ext, gemm_flavour, n, h, w, ci, co):
     from ddpt_b200.ops import gemm
     dy, wk = _bf16(n, h - 2, w - 2, co, seed=11), _bf16(co, 9 * ci, scale=(9 * co) ** -0.5, seed=12)
     wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
@@ -115,9 +115,26 @@ def test_conv3x3_dgrad(ext, n, h, w, ci, co):
     assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
 
 
+@pytest.mark.parametrize("n,h,w,ci,co", [(256, 10, 10, 256, 512), (300, 12, 12, 128, 256), (130, 9, 9, 64, 128),
+                                         (200, 11, 7, 128, 128)])
+def test_conv3x3_dgrad_skips_out_of_range_taps(ext, gemm_flavour, n, h, w, ci, co):
+    """Batches >= 128 pick one-pixel bricks over 128 images; border pixels then run only the filter taps that reach
+    them (persistent kernels, incl. the CTA-pair union / interleave logic and the resident-weight tap counters)."""
+    from ddpt_b200.ops import gemm
+    assert gemm.pick_box_dgrad(1024, 10, 10, 3, 3) == (128, 1, 1)
+    dy, wk = _bf16(n, h - 2, w - 2, co, seed=21), _bf16(co, 9 * ci, scale=(9 * co) ** -0.5, seed=22)
+    wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    want = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt)
+    dx = gemm.conv_dgrad(dy, wk, 3, 3)
+    assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
+    # per-pixel check: a skipped tap that was needed would zero out whole border rows/columns
+    err = (dx.permute(0, 3, 1, 2).float() - want).abs().amax(dim=(0, 1))
+    assert float(err.max()) < 0.05 * float(want.abs().max()), err
+
+
 @pytest.mark.parametrize("n,h,w,ci,co", [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (4, 10, 10, 256, 512),
                                          (3, 9, 13, 64, 128)])
-def test_conv3x3_wgrad(ext, n, h, w, ci, co):
+def test_conv3x3_wgrad(ext, gemm_flavour, n, h, w, ci, co):
     from ddpt_b200.ops import gemm
     dy, x = _bf16(n, h - 2, w - 2, co, seed=13), _bf16(n, h, w, ci, seed=14)
     xg = x.float().permute(0, 3, 1, 2).requires_grad_(True)
@@ -130,7 +147,7 @@ def test_conv3x3_wgrad(ext, n, h, w, ci, co):
             assert _rel_err(dw, want) < 2e-3, (split, mt)
 
 
-def test_toy_net_tail_batch_sizes(ext):
+def test_toy_net_tail_batch_sizes(ext, gemm_flavour):
     """drop_last=False tails of the reference: 304 / 332 / 608 / 664 / 784 rows."""
     from ddpt_b200.ops import gemm
     wk = _bf16(128, 9 * 64, scale=0.05, seed=15)

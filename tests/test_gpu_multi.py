@@ -74,38 +74,56 @@ def _allreduce_vs_nccl(rank, world, provider):
     dev = torch.device("cuda", rank)
     n = 64 * 1024 * 1024 // 4
     region = SymmetricRegion(n + 1024, dev)
-    info = {"provider": region.provider, "multicast": region.mc_ptr != 0}
+    info = {"provider": region.provider, "multicast": region.mc_ptr != 0, "checked": []}
     state = torch.tensor([8.0, 0.125, 0.0, 0.0, 0.0], device=dev)
+
+    def call(offset, numel, channel, algo, wire):
+        ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, region.scratch_ptrs,
+                            region.mc_scratch_ptr, rank, offset, numel, state, state[2:3], channel, algo, wire, 0, 20000)
+
     algos = [1, 2] + ([3] if region.mc_ptr else [])
-    for algo in algos:
-        for numel in (16 * 1024, 64 * 1024, 1024 * 1024, 16 * 1024 * 1024):
-            if algo == 1 and numel > 64 * 1024:
-                continue
-            g = torch.Generator(device=dev).manual_seed(1000 * rank + numel % 977 + algo)
-            src = torch.randn(numel, device=dev, generator=g)
-            region.tensor[256:256 + numel].copy_(src)
-            want = src.clone()
-            dist.all_reduce(want)
-            want.mul_(0.125 / world)
-            torch.cuda.synchronize(); dist.barrier()
-            for it in range(3):                                        # back-to-back: flag reuse
-                if it:
+    for wire in (0, 1):
+        for algo in algos:
+            for numel in (16 * 1024, 64 * 1024 - 64 * 8, 1024 * 1024, 16 * 1024 * 1024):
+                if algo == 1 and numel > 64 * 1024:
+                    continue
+                g = torch.Generator(device=dev).manual_seed(1000 * rank + numel % 977 + algo)
+                src = torch.randn(numel, device=dev, generator=g)
+                want = src.bfloat16().float() if wire else src.clone()
+                dist.all_reduce(want)
+                want.mul_(0.125 / world)
+                for it in range(3):                                        # back-to-back: epochs / slot parity
                     region.tensor[256:256 + numel].copy_(src)
                     torch.cuda.synchronize(); dist.barrier()
-                ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, rank, 256, numel, state,
-                                    state[2:3], 2, algo, 0, 20000)
-                torch.cuda.synchronize()
-                torch.testing.assert_close(region.tensor[256:256 + numel], want, rtol=2e-5, atol=2e-5)
-            assert float(state[2]) == 0.0
-    # overflow on one rank reaches everyone
-    region.tensor[:4096].fill_(1.0)
-    if rank == world - 1:
-        region.tensor[77] = float("inf")
-    torch.cuda.synchronize(); dist.barrier()
-    ext.fused_allreduce(region.peer_ptrs, region.signal_ptrs, region.mc_ptr, rank, 0, 4 * 1024 * 1024, state,
-                        state[2:3], 1, 2, 0, 20000)
-    torch.cuda.synchronize()
-    assert float(state[2]) == 1.0
+                    call(256, numel, 2, algo, wire)
+                    torch.cuda.synchronize()
+                    got = region.tensor[256:256 + numel]
+                    if wire and algo != 1:
+                        torch.testing.assert_close(got, want, rtol=2 ** -7, atol=1e-6)
+                    else:
+                        torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+                    # bit-identical across ranks
+                    mine = got.view(torch.int32).clone()
+                    ref = mine.clone()
+                    dist.broadcast(ref, 0)
+                    assert torch.equal(mine, ref), f"rank {rank} differs from rank 0 (algo {algo}, wire {wire})"
+                assert float(state[2]) == 0.0
+                info["checked"].append((wire, algo, numel))
+    # overflow on one rank reaches everyone (large bucket, many CTAs), then clears
+    for wire in (0, 1):
+        region.tensor[:4 * 1024 * 1024].fill_(1.0)
+        if rank == world - 1:
+            region.tensor[4 * 1024 * 1024 - 3] = float("inf")
+        torch.cuda.synchronize(); dist.barrier()
+        call(0, 4 * 1024 * 1024, 1, 0, wire)
+        torch.cuda.synchronize()
+        assert float(state[2]) == 1.0
+        state[2] = 0.0
+        region.tensor[:4 * 1024 * 1024].fill_(1.0)
+        torch.cuda.synchronize(); dist.barrier()
+        call(0, 4 * 1024 * 1024, 1, 0, wire)
+        torch.cuda.synchronize()
+        assert float(state[2]) == 0.0
     return info
 
 
@@ -120,7 +138,7 @@ def test_fused_allreduce_matches_nccl(provider):
             pytest.skip(f"torch symmetric memory unavailable on this box: {str(e)[-300:]}")
         raise
     assert all(i["provider"] == provider for i in infos)
-    print("symmetric memory:", infos[0])
+    print("symmetric memory:", {k: v for k, v in infos[0].items() if k != "checked"}, len(infos[0]["checked"]), "cases")
 
 
 def _ddp_autograd_matches_nccl(rank, world):
@@ -191,3 +209,111 @@ def test_engine_world2_ranks_stay_bit_identical():
     _need_gpus(2)
     out = run_gpu_ranks(_engine_ranks_identical, min(torch.cuda.device_count(), 8))
     print(out[0])
+
+
+def _engine_pg_matches_fused(rank, world):
+    """with comm='pg' the step engine must not all-reduce bucket 0 while the side-stream weight
+    gradient is still being written.  Parameters after N steps must equal the comm='fused' run bit for bit on
+    the fp32 wire (both are exact fp32 sums / world at world 2)."""
+    import torch.nn as nn
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    from ddpt_b200.utils import same_seeds
+    dev = torch.device("cuda", rank)
+    results = {}
+    for comm in ("pg", "fused"):
+        amp.reset()
+        same_seeds(11)
+        model = Toy_Net().to(dev)
+        opt = Lookahead(SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True), k=3, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+        ddp = DDP(model, device_ids=[rank], comm=comm)
+        assert ddp.comm == comm
+        loss_fn = nn.CrossEntropyLoss()
+        assert ops.attach_step_engine(ddp, loss_fn, opt)
+        eng = ddp._ddpt_step_engine
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        ddp.train(); eng.begin_pass()
+        for step in range(6):
+            x = torch.randint(0, 256, (512, 1, 28, 28), device=dev, generator=g, dtype=torch.uint8)
+            y = (x.float().mean((1, 2, 3)) > 127.5).long() + 2 * (x[:, 0, 0, 0] > 127).long()
+            eng.run(x, y, True)
+        eng.end_pass()
+        results[comm] = torch.cat([p.detach().float().reshape(-1).clone() for p in model.parameters()])
+        gathered = [torch.empty_like(results[comm]) for _ in range(world)]
+        dist.all_gather(gathered, results[comm])
+        assert all(torch.equal(gathered[0], t) for t in gathered), f"ranks diverged with comm={comm}"
+    diff = (results["pg"] - results["fused"]).abs().max().item()
+    scale = results["fused"].abs().max().item()
+    assert diff <= 1e-5 * scale, (diff, scale)
+    return diff
+
+
+def test_engine_pg_backend_waits_for_side_stream_gradients():
+    _need_gpus(2)
+    print("max |pg - fused| parameter difference:", run_gpu_ranks(_engine_pg_matches_fused, 2))
+
+
+def _buffers_broadcast_by_our_kernel(rank, world):
+    import torch.nn as nn
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(rank)
+    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Flatten(), nn.Linear(8 * 6 * 6, 4)).to(dev)
+    bn = net[1]
+    bn.running_mean.fill_(float(rank + 1)); bn.running_var.fill_(float(10 * (rank + 1))); bn.num_batches_tracked.fill_(rank + 5)
+    ddp = DDP(net, device_ids=[rank], comm="fused", bucket_cap_mb=0.001)
+    # constructor: rank 0's parameters and buffers everywhere, through our broadcast kernel
+    assert float(bn.running_mean[0]) == 1.0 and float(bn.running_var[3]) == 10.0 and int(bn.num_batches_tracked) == 5
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    ref = flat.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref)
+    b0 = ddp.backend.broadcasts
+    # every grad-enabled forward re-broadcasts rank 0's buffers (torch DDP semantics, reference utils/process.py:20);
+    # eval-mode BatchNorm so the forward itself does not touch the statistics again
+    ddp.eval()
+    for step in range(3):
+        bn.running_mean.add_(rank * 0.5 + step)               # ranks drift ...
+        bn.num_batches_tracked.add_(rank)
+        x = torch.randn(4, 3, 8, 8, device=dev)
+        ddp(x).sum().backward()
+        torch.cuda.synchronize()
+        got = bn.running_mean.clone(); ref = got.clone(); dist.broadcast(ref, 0)
+        assert torch.equal(got, ref), f"step {step}: rank {rank} running_mean differs from rank 0"
+        assert int(bn.num_batches_tracked) == 5                # ... and are pulled back to rank 0's values
+    assert ddp.backend.broadcasts - b0 == 3
+    sd = ddp.state_dict()
+    assert sd["module.1.num_batches_tracked"].dtype == torch.int64
+    return ddp.backend.provider
+
+
+def test_buffer_and_parameter_broadcast_use_the_symm_kernel():
+    _need_gpus(2)
+    run_gpu_ranks(_buffers_broadcast_by_our_kernel, min(torch.cuda.device_count(), 4))
+
+
+def _odd_world_buckets(rank, world):
+    """buckets are padded to 32 B x world, so 3 / 5 / 6 / 7 GPUs work with the fused back end."""
+    import torch.nn as nn
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(37, 301), nn.ReLU(), nn.Linear(301, 10)).to(dev)
+    for wire in ("fp32", "bf16"):
+        ddp = DDP(net, device_ids=[rank], comm="fused", bucket_cap_mb=0.02, comm_wire=wire, tail_bucket_kb=1)
+        assert all(b.numel % (8 * world) == 0 for b in ddp.buckets) and len(ddp.buckets) >= 2
+        x = torch.randn(8, 37, device=dev) + rank
+        ddp.zero_grad()
+        ddp(x).sum().backward()
+        torch.cuda.synchronize()
+        for p in net.parameters():
+            ref = p.grad.clone(); dist.broadcast(ref, 0)
+            assert torch.equal(p.grad, ref)
+    return True
+
+
+def test_fused_backend_on_three_gpus():
+    _need_gpus(3)
+    run_gpu_ranks(_odd_world_buckets, 3)

@@ -55,14 +55,24 @@ def test_checkpoint_layout_matches_shipped_artifact(reference_root, tmp_path):
 def test_bucket_plan_matches_ddp_steady_state():
     m = Toy_Net()
     params = list(m.parameters())
-    buckets = plan_buckets(params, 25.0)
+    # torch DDP's steady-state layout when the tail split is off ...
+    buckets = plan_buckets(params, 25.0, tail_bucket_bytes=0)
     assert [b.nbytes for b in buckets] == [16_803_880, 6_206_976]
     names = [n for n, _ in m.named_parameters()]
     assert [names[i] for i in buckets[0].param_indices] == [
         "dense.4.bias", "dense.4.weight", "dense.2.bias", "dense.2.weight", "dense.1.bias", "dense.1.weight"]
     assert all(o % 4 == 0 for b in buckets for o in b.offsets) and all(b.numel % 128 == 0 for b in buckets)
+    # ... and by default the last-ready gradients (conv.1 / conv.0: nothing left to overlap with) get their own
+    # latency-sized bucket; everything else keeps DDP's order
+    buckets = plan_buckets(params, 25.0)
+    assert [b.nbytes for b in buckets] == [16_803_880, 6_203_904, 3_072]
+    assert [names[i] for i in buckets[2].param_indices] == ["conv.1.bias", "conv.1.weight", "conv.0.bias", "conv.0.weight"]
+    assert sorted(i for b in buckets for i in b.param_indices) == list(range(22))
+    for world in (2, 3, 5, 6, 7, 8):        # every bucket splits into 16-byte vectors (fp32 or bf16) per rank
+        plan = plan_buckets(params, 25.0, world_size=world)
+        assert all(b.numel % (8 * world) == 0 and b.numel % 128 == 0 and b.start % 128 == 0 for b in plan)
     big = plan_buckets(list(resnet50().parameters()), 25.0)
-    assert len(big) >= 4 and all(b.nbytes <= 36 * 2**20 for b in big[1:])
+    assert len(big) >= 4 and all(b.nbytes <= 36 * 2**20 for b in big[1:]) and big[-1].nbytes <= 256 * 1024
 
 
 def test_tensorboard_layout(tmp_path):
