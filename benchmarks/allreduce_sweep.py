@@ -34,7 +34,9 @@ def main():
     nccl_bf16 = nccl_buf.bfloat16()
     region.tensor.copy_(nccl_buf)
 
-    def timed(fn, iters):
+    def timed(fn, iters, reps=1):
+        """Median device time of one call.  `reps` back-to-back calls between the events take the host's launch
+        latency (~10 us of Python per call) out of small-bucket numbers: what a CUDA graph replays is the kernel."""
         for _ in range(3):
             fn()
         ts = []
@@ -42,9 +44,12 @@ def main():
             flush.zero_()
             torch.cuda.synchronize(); dist.barrier()
             s, e = torch.cuda.Event(True), torch.cuda.Event(True)
-            s.record(); fn(); e.record()
+            s.record()
+            for _ in range(reps):
+                fn()
+            e.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
+            ts.append(s.elapsed_time(e) / reps)
         t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -59,29 +64,35 @@ def main():
     while size <= a.max_mb * 1024 * 1024:
         n = size // 4
         row = {"bytes": size}
+        reps = 10 if size <= 4 * 1024 * 1024 else 1       # small buckets: pipelined launches (kernel time, not host time)
         variants = {"f32_auto": (0, 0, 0), "bf16_auto": (0, 1, 0), "f32_twoshot_p2p": (2, 0, 0),
                     "bf16_twoshot_p2p": (2, 1, 0)}
+        if region.mc_ptr and n > 64 * 1024:
+            variants["f32_multimem"] = (3, 0, 0)
+            variants["bf16_multimem"] = (3, 1, 0)
         if size >= 4 * 1024 * 1024:
-            variants["f32_auto_b64"] = (0, 0, 64)
-            variants["bf16_auto_b64"] = (0, 1, 64)
-            variants["bf16_auto_b16"] = (0, 1, 16)
+            variants["f32_auto_b128"] = (0, 0, 128)
+            variants["bf16_auto_b128"] = (0, 1, 128)
+            variants["f32_auto_b32"] = (0, 0, 32)
         for name, (algo, wire, blocks) in variants.items():
-            ms = timed(fused(n, algo, wire, blocks), a.iters)
+            ms = timed(fused(n, algo, wire, blocks), a.iters, reps)
             row[f"fused_{name}_us"] = round(ms * 1e3, 2)
             row[f"fused_{name}_busGBs"] = round(2 * (world - 1) / world * size / (ms * 1e-3) / 1e9, 1)
         view = nccl_buf[:n]
-        ms = timed(lambda: dist.all_reduce(view), a.iters)
+        ms = timed(lambda: dist.all_reduce(view), a.iters, reps)
         row["nccl_us"] = round(ms * 1e3, 2)
         row["nccl_busGBs"] = round(2 * (world - 1) / world * size / (ms * 1e-3) / 1e9, 1)
         v16 = nccl_bf16[:n]
-        ms = timed(lambda: dist.all_reduce(v16), a.iters)
+        ms = timed(lambda: dist.all_reduce(v16), a.iters, reps)
         row["nccl_bf16_us"] = round(ms * 1e3, 2)          # same gradient count sent as bf16 (no cast / scale / check)
         rows.append(row)
         size *= 4
     if rank == 0:
         out = {"world": world, "provider": region.provider, "multicast": bool(region.mc_ptr), "rows": rows,
                "link_GBs_measured_per_direction": 770, "link_GBs_nominal": 900,
-               "note": "auto = one-shot push <= 256 KiB, else multimem two-shot when multicast is mapped"}
+               "note": "auto = one-shot push <= 256 KiB, else two-shot: peer loads at 2 GPUs, multimem (NVLS) from 4; "
+                       "buckets <= 4 MB are timed as 10 back-to-back launches / 10 (host launch latency excluded, as in "
+                       "a CUDA graph); _bN = N CTAs of 256 threads (default 64)"}
         print(json.dumps(out, indent=1))
         if a.out:
             os.makedirs(os.path.dirname(a.out), exist_ok=True)

@@ -66,11 +66,23 @@ def main():
                                    flush=flush)
                         rows.append(dict(op=f"{name}.wgrad{'.multitap' if mt else ''}", block_n=bn, ms=t,
                                          tflops=flops / t / 1e9))
-            # library reference for the same layer (channels_last bf16)
+            # data gradient with / without skipping out-of-range filter taps (one-pixel bricks over 128 images)
+            for skip in ("1", "0"):
+                os.environ["DDPT_DGRAD_SKIP_TAPS"] = skip
+                t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3), flush=flush)
+                rows.append(dict(op=f"{name}.dgrad.default.skip_taps={skip}", ms=t, tflops=flops / t / 1e9))
+            os.environ.pop("DDPT_DGRAD_SKIP_TAPS", None)
+            # library reference for the same layer (channels_last bf16): forward, data gradient, weight gradient
             xn = x.permute(0, 3, 1, 2)
             wn = wk.view(co, 3, 3, ci).permute(0, 3, 1, 2)
+            dyn = dy.permute(0, 3, 1, 2)
             t = timeit(lambda: F.conv2d(xn, wn), flush=flush)
             rows.append(dict(op=f"{name}.fwd.cudnn", ms=t, tflops=flops / t / 1e9))
+            cb = torch.ops.aten.convolution_backward
+            t = timeit(lambda: cb(dyn, xn, wn, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False]), flush=flush)
+            rows.append(dict(op=f"{name}.dgrad.cudnn", ms=t, tflops=flops / t / 1e9))
+            t = timeit(lambda: cb(dyn, xn, wn, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [False, True, False]), flush=flush)
+            rows.append(dict(op=f"{name}.wgrad.cudnn", ms=t, tflops=flops / t / 1e9))
         x = torch.randn(B, 8192, device="cuda").bfloat16()
         w1 = (torch.randn(512, 8192, device="cuda") * 0.01).bfloat16()
         dy = torch.randn(B, 512, device="cuda").bfloat16()
@@ -86,6 +98,10 @@ def main():
         rows.append(dict(op="dense.1.wgrad", ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: x @ w1.t(), flush=flush)
         rows.append(dict(op="dense.1.fwd.cublas", ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: dy @ w1, flush=flush)
+        rows.append(dict(op="dense.1.dgrad.cublas", ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: dy.t() @ x, flush=flush)
+        rows.append(dict(op="dense.1.wgrad.cublas", ms=t, tflops=fl / t / 1e9))
         res["kernels"] = rows
     except Exception as exc:  # keep the library baseline even if our kernels fail
         import traceback
@@ -109,23 +125,27 @@ def main():
         t = timeit(step, iters=20, warmup=5)
         res["library_step_ms"] = t
         res["library_img_per_s"] = B / t * 1e3
-        g = torch.cuda.CUDAGraph()
-        opt2 = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, capturable=False)
+        # the same step as ONE CUDA graph (no launch gaps): the honest kernel-level library baseline.  Whole-network
+        # capture recipe: warm up on a side stream (momentum buffers exist), then capture fwd + bwd + optimizer.
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
                 step()
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
         try:
+            g = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(g):
-                opt.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     out = model.forward_reference(xin)
                 loss = F.cross_entropy(out.float(), tgt) / B
                 loss.backward()
-            t = timeit(g.replay, iters=20, warmup=3)
-            res["library_graph_fwdbwd_ms"] = t
+                opt.step()
+            t = timeit(g.replay, iters=30, warmup=5)
+            res["library_graph_step_ms"] = t
+            res["library_graph_img_per_s"] = B / t * 1e3
         except Exception as exc:
             res["library_graph_error"] = repr(exc)
     except Exception:

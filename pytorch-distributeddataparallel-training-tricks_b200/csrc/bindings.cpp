@@ -155,7 +155,16 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
   p.out = out.data_ptr(); p.ld_out = out.stride(0); p.out_fp32 = out.scalar_type() == at::kFloat;
   if (bias.has_value()) { check_cuda(*bias, "bias", at::kFloat); TORCH_CHECK(bias->numel() >= p.n_total); p.bias = bias->data_ptr<float>(); }
   p.relu = relu ? 1 : 0;
-  if (stat_partials.has_value()) { check_cuda(*stat_partials, "stat_partials", at::kFloat); p.stat_partials = stat_partials->data_ptr<float>(); }
+  if (stat_partials.has_value()) {
+    if (stat_partials->scalar_type() == at::kDouble) {     // fp64 accumulators [2][N]: epilogues add, no partial rows
+      check_cuda(*stat_partials, "stat_partials", at::kDouble);
+      TORCH_CHECK(stat_partials->numel() >= 2 * p.n_total && split_k <= 1, "stat accumulators: need [2][N] doubles, no split-K");
+      p.stat_accum = stat_partials->data_ptr<double>();
+    } else {
+      check_cuda(*stat_partials, "stat_partials", at::kFloat);
+      p.stat_partials = stat_partials->data_ptr<float>();
+    }
+  }
   p.split_k = (int)split_k;
   if (p.stat_partials != nullptr) {
     const int64_t tiles = (int64_t)((p.out_w + p.box_w - 1) / p.box_w) * ((p.out_h + p.box_h - 1) / p.box_h) *

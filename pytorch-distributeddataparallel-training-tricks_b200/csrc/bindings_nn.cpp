@@ -27,13 +27,18 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
   TORCH_CHECK(weight.numel() == 64 * 9 && bias.numel() == 64 && y.numel() == (int64_t)batch * 26 * 26 * 64);
   c10::cuda::CUDAGuard g(x.device());
   float* part = nullptr;
-  if (partials.has_value()) {
+  double* accum = nullptr;
+  if (partials.has_value() && partials->scalar_type() == at::kDouble) {     // fp64 accumulators [2][64]
+    need(*partials, at::kDouble, "partials");
+    TORCH_CHECK(partials->numel() >= 2 * 64);
+    accum = partials->data_ptr<double>();
+  } else if (partials.has_value()) {
     need(*partials, at::kFloat, "partials");
     TORCH_CHECK(partials->numel() >= ddpt::conv0_partial_rows() * 2 * 64);
     part = partials->data_ptr<float>();
   }
   return ddpt::launch_conv0_fwd(x.data_ptr(), x.scalar_type() == at::kByte, weight.data_ptr<float>(),
-                                bias.data_ptr<float>(), bfm(y), part, batch, cur());
+                                bias.data_ptr<float>(), bfm(y), part, accum, batch, cur());
 }
 
 void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db) {
@@ -77,14 +82,20 @@ void bn_eval_coeffs(at::Tensor gamma, at::Tensor beta, at::Tensor running_mean, 
                               running_var.data_ptr<float>(), (float)eps, c, co, co + c, cur());
 }
 
+// accum (optional, fp64 [2][C]): fused statistics -- the kernel derives scale/shift itself, writes them (+ mean, invstd)
+// into `coeffs` for the backward pass and updates running_mean / running_var / num_batches_tracked.
 void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bool flatten_chw,
-                  c10::optional<at::Tensor> q_out, c10::optional<at::Tensor> q_scale) {
+                  c10::optional<at::Tensor> q_out, c10::optional<at::Tensor> q_scale,
+                  c10::optional<at::Tensor> accum, double count, c10::optional<at::Tensor> gamma,
+                  c10::optional<at::Tensor> beta, double eps, double momentum,
+                  c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                  c10::optional<at::Tensor> nbt) {
   need(y, at::kBFloat16, "y"); need(coeffs, at::kFloat, "coeffs"); need(out, at::kBFloat16, "out");
   TORCH_CHECK(y.dim() == 4);
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(out.numel() == (pool ? y.numel() / 4 : y.numel()));
   c10::cuda::CUDAGuard g(y.device());
-  const float* co = coeffs.data_ptr<float>();
+  float* co = coeffs.data_ptr<float>();
   uint8_t* qd = nullptr; uint8_t* qs = nullptr;
   if (q_out.has_value()) {
     TORCH_CHECK(q_scale.has_value());
@@ -92,7 +103,24 @@ void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bo
     TORCH_CHECK(q_out->numel() == out.numel() && q_scale->numel() == out.numel() / 32);
     qd = q_out->data_ptr<uint8_t>(); qs = q_scale->data_ptr<uint8_t>();
   }
-  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, cur());
+  ddpt::BnFusedFwd f{};
+  if (accum.has_value()) {
+    need(*accum, at::kDouble, "accum"); TORCH_CHECK(accum->numel() >= 2 * c && gamma.has_value() && beta.has_value());
+    need(*gamma, at::kFloat, "gamma"); need(*beta, at::kFloat, "beta");
+    TORCH_CHECK(gamma->numel() == c && beta->numel() == c && coeffs.numel() >= 4 * c && count > 0);
+    f.accum = accum->data_ptr<double>(); f.count = count; f.inv_count = 1.0 / count;
+    f.unbias = count > 1.0 ? (float)(count / (count - 1.0)) : 1.0f;
+    f.gamma = gamma->data_ptr<float>(); f.beta = beta->data_ptr<float>();
+    f.eps = (float)eps; f.momentum = (float)momentum;
+    f.out = ddpt::BnCoeffs{co, co + c, co + 2 * c, co + 3 * c};
+    if (running_mean.has_value()) {
+      TORCH_CHECK(running_var.has_value());
+      need(*running_mean, at::kFloat, "running_mean"); need(*running_var, at::kFloat, "running_var");
+      f.running_mean = running_mean->data_ptr<float>(); f.running_var = running_var->data_ptr<float>();
+    }
+    if (nbt.has_value()) { TORCH_CHECK(nbt->scalar_type() == at::kLong); f.num_batches_tracked = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
+  }
+  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, f, cur());
 }
 
 void chw_to_hwc(at::Tensor in, at::Tensor out, int64_t c, int64_t p) {
@@ -104,13 +132,20 @@ void chw_to_hwc(at::Tensor in, at::Tensor out, int64_t c, int64_t p) {
 
 int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor partials, bool pool, bool flatten_chw) {
   need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
-  need(partials, at::kFloat, "partials");
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(g_in.numel() == (pool ? y.numel() / 4 : y.numel()));
-  TORCH_CHECK(partials.numel() >= (int64_t)ddpt::bn_bwd_partial_rows() * 2 * c);
+  float* part = nullptr; double* accum = nullptr;
+  if (partials.scalar_type() == at::kDouble) {            // fp64 accumulators [2][C] (zeroed by the caller)
+    need(partials, at::kDouble, "partials"); TORCH_CHECK(partials.numel() >= 2 * c);
+    accum = partials.data_ptr<double>();
+  } else {
+    need(partials, at::kFloat, "partials");
+    TORCH_CHECK(partials.numel() >= (int64_t)ddpt::bn_bwd_partial_rows() * 2 * c);
+    part = partials.data_ptr<float>();
+  }
   c10::cuda::CUDAGuard guard(y.device());
   const float* co = coeffs.data_ptr<float>();
-  return ddpt::launch_bn_bwd_reduce(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, partials.data_ptr<float>(), n,
+  return ddpt::launch_bn_bwd_reduce(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, part, accum, n,
                                     h, w, c, pool, flatten_chw, cur());
 }
 
@@ -127,8 +162,12 @@ void bn_bwd_finalize(at::Tensor partials, int64_t num_partials, double count, at
                                bwd_coef.data_ptr<float>(), accumulate, cur());
 }
 
+// accum (optional, fp64 [2][C] from bn_bwd_reduce): fused statistics -- the kernel derives its coefficients itself and
+// writes dgamma / dbeta (bwd_coef is then unused).
 void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor bwd_coef, at::Tensor dy,
-                  c10::optional<at::Tensor> dbias, bool pool, bool flatten_chw) {
+                  c10::optional<at::Tensor> dbias, bool pool, bool flatten_chw, c10::optional<at::Tensor> accum,
+                  double count, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> dgamma,
+                  c10::optional<at::Tensor> dbeta) {
   need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
   need(bwd_coef, at::kFloat, "bwd_coef"); need(dy, at::kBFloat16, "dy");
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
@@ -137,8 +176,17 @@ void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor b
   const float* co = coeffs.data_ptr<float>();
   float* db = nullptr;
   if (dbias.has_value()) { need(*dbias, at::kFloat, "dbias"); TORCH_CHECK(dbias->numel() == c); db = dbias->data_ptr<float>(); }
+  ddpt::BnFusedBwd f{};
+  if (accum.has_value()) {
+    need(*accum, at::kDouble, "accum");
+    TORCH_CHECK(accum->numel() >= 2 * c && gamma.has_value() && dgamma.has_value() && dbeta.has_value() && count > 0);
+    need(*gamma, at::kFloat, "gamma"); need(*dgamma, at::kFloat, "dgamma"); need(*dbeta, at::kFloat, "dbeta");
+    TORCH_CHECK(gamma->numel() == c && dgamma->numel() == c && dbeta->numel() == c);
+    f.accum = accum->data_ptr<double>(); f.count = count; f.inv_count = 1.0 / count; f.gamma = gamma->data_ptr<float>();
+    f.dgamma = dgamma->data_ptr<float>(); f.dbeta = dbeta->data_ptr<float>();
+  }
   ddpt::launch_bn_bwd_apply(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, bwd_coef.data_ptr<float>(), bfm(dy), db,
-                            n, h, w, c, pool, flatten_chw, cur());
+                            f, n, h, w, c, pool, flatten_chw, cur());
 }
 
 // Forward-only when da is None.  dlogits: if given, used instead of the fused cross-entropy gradient.
@@ -229,10 +277,16 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("conv0_wgrad", &conv0_wgrad);
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_eval_coeffs", &bn_eval_coeffs);
-  m.def("bn_relu_pool", &bn_relu_pool);
+  m.def("bn_relu_pool", &bn_relu_pool, py::arg("y"), py::arg("coeffs"), py::arg("out"), py::arg("pool"),
+        py::arg("flatten_chw"), py::arg("q_out") = py::none(), py::arg("q_scale") = py::none(),
+        py::arg("accum") = py::none(), py::arg("count") = 0.0, py::arg("gamma") = py::none(),
+        py::arg("beta") = py::none(), py::arg("eps") = 1e-5, py::arg("momentum") = 0.1,
+        py::arg("running_mean") = py::none(), py::arg("running_var") = py::none(), py::arg("nbt") = py::none());
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_finalize", &bn_bwd_finalize);
-  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_bwd_apply", &bn_bwd_apply, py::arg("y"), py::arg("g"), py::arg("coeffs"), py::arg("bwd_coef"), py::arg("dy"),
+        py::arg("dbias"), py::arg("pool"), py::arg("flatten_chw"), py::arg("accum") = py::none(), py::arg("count") = 0.0,
+        py::arg("gamma") = py::none(), py::arg("dgamma") = py::none(), py::arg("dbeta") = py::none());
   m.def("chw_to_hwc", &chw_to_hwc);
   m.def("head", &head);
 }

@@ -38,7 +38,11 @@
 namespace ddpt {
 namespace {
 
-constexpr int kThreads = 512;
+// 256 threads x <= 64 registers = 16 Ki registers per CTA: a communication CTA then CO-RESIDES with a persistent GEMM CTA
+// (320 threads x 144 registers = 45 Ki of the SM's 64 Ki).  The first version ran 512 x 98 registers: every SM that hosted
+// one could not accept the GEMM CTA scheduled next, and because the GEMM kernels walk static tile lists, a CTA that
+// starts 60 us late finishes 60 us late -- the overlapped all-reduce stretched the backward it was hiding under.
+constexpr int kThreads = 256;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t val) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(val) : "memory");
@@ -159,7 +163,7 @@ __device__ __forceinline__ long long push_offset(int channel, uint32_t parity, i
 
 // ---- one-shot (push) ----------------------------------------------------------------------------------------------
 template <int WIRE, bool MC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 oneshot_push_kernel(AllReduceArgs a) {
   const float scale = scale_of(a);
   const uint32_t e = epoch_begin(a);
@@ -220,7 +224,7 @@ oneshot_push_kernel(AllReduceArgs a) {
 
 // ---- two-shot (peer loads/stores or multimem) -----------------------------------------------------------------------
 template <int WIRE, bool MC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 twoshot_kernel(AllReduceArgs a) {
   const float scale = scale_of(a);
   const uint32_t e = epoch_begin(a);
@@ -229,7 +233,7 @@ twoshot_kernel(AllReduceArgs a) {
   bool bad = false;
   // kUnroll independent 16-byte vectors per thread are in flight at once: NVLink round trips are ~2 us, so
   // bandwidth is bytes-in-flight limited (blocks x 512 threads x kUnroll x 16 B x world loads).
-  constexpr int kUnroll = (WIRE == kWireBF16 && !MC) ? 4 : 8;       // the bf16 peer-load variant keeps 8 fp32 accumulators per vector
+  constexpr int kUnroll = MC ? 8 : (WIRE == kWireBF16 ? 2 : 4);     // peer-load variants hold fp32 accumulators (64-register budget)
 
   if (WIRE == kWireBF16) {
     // phase A: cast my whole bucket into my 16-bit staging (local read 4 B/elem, local write 2 B/elem)
@@ -457,7 +461,12 @@ void launch_fused_allreduce(const AllReduceArgs& args, cudaStream_t stream) {
   const bool twoshot_ok = args.numel % ((long long)vec * args.world) == 0;
   if (algo == kAlgoAuto) {
     if (have_scratch && args.numel <= kOneShotMaxElems) algo = kAlgoOneShot;
-    else algo = (bf16 ? args.mc_scratch != nullptr : args.mc_buf != nullptr) ? kAlgoMultimem : kAlgoTwoShot;
+    else {
+      // in-switch reduction pays from 4 GPUs up; between 2 GPUs every element would cross the switch twice for nothing
+      // (measured at N = 2, 64 MB: peer loads 144 us, multimem 191 us, NCCL 164 us)
+      const bool mc = bf16 ? args.mc_scratch != nullptr : args.mc_buf != nullptr;
+      algo = (mc && args.world > 2) ? kAlgoMultimem : kAlgoTwoShot;
+    }
   }
   if (algo == kAlgoOneShot && (!have_scratch || args.numel > kOneShotMaxElems))
     throw std::runtime_error("fused_allreduce: one-shot needs the scratch region and <= 64 Ki elements");
@@ -468,7 +477,7 @@ void launch_fused_allreduce(const AllReduceArgs& args, cudaStream_t stream) {
   AllReduceArgs a = args;
   if (a.timeout_ms <= 0) a.timeout_ms = 30000;
   if (algo == kAlgoOneShot) {
-    // exactly one vector per thread: block b always owns bytes [8 KiB x b, 8 KiB x (b+1)) of every push slot, whatever
+    // exactly one vector per thread: block b always owns bytes [4 KiB x b, 4 KiB x (b+1)) of every push slot, whatever
     // the bucket size, so the per-(channel, block) epoch parity is a valid double-buffer index for that range
     long long want = (args.numel / vec + kThreads - 1) / kThreads;
     const int blocks = (int)(want < 1 ? 1 : want);
@@ -477,7 +486,7 @@ void launch_fused_allreduce(const AllReduceArgs& args, cudaStream_t stream) {
   } else {
     const long long vec_per_rank = args.numel / args.world / vec;
     long long want = (vec_per_rank + kThreads - 1) / kThreads;
-    int blocks = args.blocks > 0 ? args.blocks : 32;
+    int blocks = args.blocks > 0 ? args.blocks : 64;
     if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
     if (want < blocks) blocks = (int)(want > 0 ? want : 1);
     const bool mc = algo == kAlgoMultimem;

@@ -6,7 +6,7 @@
 namespace ddpt {
 
 constexpr int kMaxRanks = 8;
-constexpr int kCommMaxBlocks = 64;          // CTAs per all-reduce launch (upper bound)
+constexpr int kCommMaxBlocks = 128;         // CTAs per all-reduce launch (upper bound)
 constexpr int kCommChannels = 8;            // independent signal regions (one per in-flight bucket)
 constexpr long long kOneShotMaxElems = 64 * 1024;   // buckets up to 256 KiB of fp32 take the one-shot (push) path
 

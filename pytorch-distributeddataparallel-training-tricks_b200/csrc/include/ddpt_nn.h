@@ -37,6 +37,10 @@ struct ConvGemmProblem {
   const float* bias;                       // optional, per output column
   int relu;
   float* stat_partials;                    // optional [num_m_tiles][2][n_total]: per-tile column sum / sum of squares
+  double* stat_accum;                      // optional [2][n_total] fp64 accumulators (zeroed by the caller): the epilogues add
+                                           // their column sums / sums of squares with red.global.add.f64 instead of writing
+                                           // partial rows, and the consumer pass derives the BatchNorm coefficients itself
+                                           // (no *_finalize launch).  Unordered adds: use stat_partials for bit-stable runs.
   int split_k;                             // K splits (fp32 output only)
 };
 

@@ -12,8 +12,11 @@ namespace ddpt {
 // x: uint8 [B,28,28] (scaled by 1/255 on the fly) or fp32 [B,28,28];  y: bf16 [B,26,26,64]
 // Returns the number of statistic partial rows written ([rows][2][64]); capacity needed: conv0_partial_rows().
 int conv0_partial_rows();
+// stat_accum (optional, fp64 [2][64], zeroed by the caller): the block sums are added there (red.global.add.f64)
+// instead of being written as partial rows.
 int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/, const float* bias,
-                     __nv_bfloat16* y, float* stat_partials /*[rows][2][64] or null*/, int batch, cudaStream_t s);
+                     __nv_bfloat16* y, float* stat_partials /*[rows][2][64] or null*/, double* stat_accum,
+                     int batch, cudaStream_t s);
 // dW [64][9], db [64] accumulated with atomics into zero-initialised (or beta=1) fp32 buffers.
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
                         cudaStream_t s);
@@ -24,6 +27,28 @@ struct BnCoeffs {          // all float [C]
   float* shift;            // beta - mean * scale
   float* mean;
   float* invstd;
+};
+// Statistics handed over as fp64 accumulators [2][C] (sum, sum of squares) filled by the producing kernel's epilogue:
+// the consuming pass derives scale/shift in its prologue (every CTA, 8 channels per thread, into shared memory) and
+// CTA 0 publishes the coefficients for the backward pass and updates the running statistics -- the bn_finalize
+// launch and its pass over hundreds of partial rows disappear from the critical path.
+struct BnFusedFwd {
+  const double* accum;     // null: use the precomputed scale/shift arguments
+  double count;            // elements per channel; the kernels only multiply (1/count and count/(count-1) come from the host:
+  double inv_count;        // fp64 divisions / square roots in every CTA's prologue cost more than the launch they replace)
+  float unbias;
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  BnCoeffs out;
+  float* running_mean; float* running_var; long long* num_batches_tracked;   // optional
+};
+// Same for the backward pass: accumulators [2][C] = sum dz, sum dz*y from bn_bwd_reduce; bn_bwd_apply derives its
+// coefficients and CTA 0 writes dgamma / dbeta.
+struct BnFusedBwd {
+  const double* accum;     // null: use the precomputed coefficient argument
+  double count, inv_count;
+  const float* gamma;
+  float* dgamma; float* dbeta;
 };
 // Fold partials into batch statistics, produce scale/shift, update running stats (momentum, unbiased var)
 // and num_batches_tracked (int64).
@@ -39,15 +64,15 @@ void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* r
 // q_out / q_scale (optional): also emit the activation as MXFP8 (e4m3 [same layout] + UE8M0 per 32 along the last dim)
 void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
                          int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
-                         cudaStream_t s);
+                         const BnFusedFwd& fused, cudaStream_t s);
 
 // ---- BatchNorm backward (two passes) ----------------------------------------------------------------------
 // Pass 1: partials[blk][0][c] = sum dz, partials[blk][1][c] = sum dz * y (finalize converts to sum dz * xhat), dz = grad of the BN output
 // after routing g through max-pool (if any) and the ReLU mask.  Returns the number of partial rows.
 int bn_bwd_partial_rows();
 int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
-                         const float* mean, const float* invstd, float* partials, int n, int h, int w, int c,
-                         int pool, int g_flatten_chw, cudaStream_t s);
+                         const float* mean, const float* invstd, float* partials, double* accum /*[2][C] or null*/,
+                         int n, int h, int w, int c, int pool, int g_flatten_chw, cudaStream_t s);
 // Fold pass-1 partials: dgamma = sum dz*xhat, dbeta = sum dz (written/accumulated into the grad arena) and the
 // three per-channel coefficients of pass 2.
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
@@ -58,8 +83,8 @@ void launch_chw_to_hwc(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int c
 // Pass 2: dy = c1 * (dz - c2 - xhat * c3) as bf16 NHWC; optionally sum dy per channel (conv bias gradient).
 void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
                          const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy,
-                         float* dbias /*[C] atomics or null*/, int n, int h, int w, int c, int pool,
-                         int g_flatten_chw, cudaStream_t s);
+                         float* dbias /*[C] atomics or null*/, const BnFusedBwd& fused, int n, int h, int w, int c,
+                         int pool, int g_flatten_chw, cudaStream_t s);
 
 // ---- classifier head: Linear(512,10) + CrossEntropy(mean)/B + argmax, forward and backward ------------------
 struct HeadArgs {

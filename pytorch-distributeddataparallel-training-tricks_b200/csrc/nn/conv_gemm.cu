@@ -44,6 +44,7 @@ struct KernelArgs {
   void* out;
   const float* bias;
   float* stat_partials;
+  double* stat_accum;
   int relu, out_fp32, a_rows_bytes;
 };
 
@@ -173,7 +174,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
       }
-      if (args.stat_partials != nullptr) {
+      if (args.stat_partials != nullptr || args.stat_accum != nullptr) {
         // column statistics over the 32 rows of this warp: transpose-reduce (31 shuffles per quantity)
         float s1[32], s2[32];
 #pragma unroll
@@ -196,9 +197,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         // lane L now holds the totals of column bitreverse-free index: column = lane (see note below)
-        float* dst = args.stat_partials + (static_cast<long long>(tile_m) * 4 + quad) * 2 * args.n_total;
-        dst[col + lane] = s1[0];
-        dst[args.n_total + col + lane] = s2[0];
+        if (args.stat_accum != nullptr) {
+          atomicAdd(args.stat_accum + col + lane, (double)s1[0]);
+          atomicAdd(args.stat_accum + args.n_total + col + lane, (double)s2[0]);
+        } else {
+          float* dst = args.stat_partials + (static_cast<long long>(tile_m) * 4 + quad) * 2 * args.n_total;
+          dst[col + lane] = s1[0];
+          dst[args.n_total + col + lane] = s2[0];
+        }
       }
       if (args.relu) {
 #pragma unroll
@@ -255,7 +261,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.a_h_off = p.a_h_off; a.a_w_off = p.a_w_off;
   a.k_chunks = p.a_c / kBlockK;
   a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
-  a.stat_partials = p.stat_partials; a.relu = p.relu; a.out_fp32 = p.out_fp32;
+  a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
 
   if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)

@@ -46,6 +46,7 @@ struct HaloArgs {
   void* out;
   const float* bias;
   float* stat_partials;
+  double* stat_accum;
   int relu, out_fp32;
 };
 
@@ -233,7 +234,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
         }
-        if (args.stat_partials != nullptr) {
+        if (args.stat_partials != nullptr || args.stat_accum != nullptr) {
           float s1[32], s2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -284,7 +285,15 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (args.stat_partials != nullptr) {
+    if (args.stat_accum != nullptr) {
+      const int my_tile_n = blockIdx.x % num_n_tiles;
+#pragma unroll
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int col = my_tile_n * BN + (half * kChunksPerWarp + cc) * 32 + lane;
+        atomicAdd(args.stat_accum + col, (double)acc_s1[cc]);
+        atomicAdd(args.stat_accum + args.n_total + col, (double)acc_s2[cc]);
+      }
+    } else if (args.stat_partials != nullptr) {
       const int my_tile_n = blockIdx.x % num_n_tiles;
       float* dst = args.stat_partials + (static_cast<long long>(blockIdx.x) * 4 + quad) * 2 * args.n_total;
       for (int tn2 = 0; tn2 < num_n_tiles; ++tn2) {
@@ -328,7 +337,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   // the 16-group view may read past the loaded rows when box_h * box_n < 16: keep that inside the slot
   const int view_rows = (16 + (p.taps_h - 1) * p.box_n) * 8;
   a.a_slot_bytes = round_up((view_rows > halo_rows ? view_rows : halo_rows) * 128, 1024);
-  a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias; a.stat_partials = p.stat_partials;
+  a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias; a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum;
   a.relu = p.relu; a.out_fp32 = p.out_fp32;
 
   const int total_kb = p.taps_h * p.taps_w * a.k_chunks;

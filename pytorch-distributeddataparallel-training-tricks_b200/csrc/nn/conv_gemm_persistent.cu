@@ -50,6 +50,7 @@ struct KernelArgs {
   void* out;
   const float* bias;
   float* stat_partials;
+  double* stat_accum;
   int relu, out_fp32, a_rows_bytes;
   int stages;                   // pipeline depth (stage = kbs K blocks of A [+ B unless resident])
   int kbs;                      // K blocks (tap x 64-channel chunk) per pipeline stage: amortises the barrier round trip
@@ -345,7 +346,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
         }
-        if (args.stat_partials != nullptr) {
+        if (args.stat_partials != nullptr || args.stat_accum != nullptr) {
           float s1[32], s2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -399,7 +400,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         if (MC > 1) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
       }
     }
-    if (args.stat_partials != nullptr) {
+    if (args.stat_accum != nullptr) {
+      // fp64 accumulators shared by all CTAs (4 quadrants x 148 CTAs adds per column: negligible next to the tile loop)
+      const int my_tile_n = unit0 % num_n_tiles;
+#pragma unroll
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int col = my_tile_n * BN + (half * kChunksPerWarp + cc) * 32 + lane;
+        atomicAdd(args.stat_accum + col, (double)acc_s1[cc]);
+        atomicAdd(args.stat_accum + args.n_total + col, (double)acc_s2[cc]);
+      }
+    } else if (args.stat_partials != nullptr) {
       // one row group per CTA: [blockIdx.x][quad][2][n_total]; columns of other column blocks are written as 0
       const int my_tile_n = unit0 % num_n_tiles;
       float* dst = args.stat_partials + (static_cast<long long>(blockIdx.x) * 4 + quad) * 2 * args.n_total;
@@ -455,7 +465,7 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.a_h_off = p.a_h_off; a.a_w_off = p.a_w_off;
   a.k_chunks = p.a_c / kBlockK;
   a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
-  a.stat_partials = p.stat_partials; a.relu = p.relu; a.out_fp32 = p.out_fp32;
+  a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
   a.a_w = p.a_w; a.a_h = p.a_h;
   a.pair_interleave = (MC == 2 && tiles_n % 2 == 0 && p.taps_h * p.taps_w > 1) ? 1 : 0;

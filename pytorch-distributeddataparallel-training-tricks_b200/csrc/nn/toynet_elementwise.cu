@@ -92,7 +92,7 @@ __device__ __forceinline__ void load_image(const void* x, int x_is_u8, int img, 
 __global__ void __launch_bounds__(kThreads)
 conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restrict__ weight,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ partials,
-                 int batch) {
+                 double* __restrict__ accum, int batch) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
@@ -130,7 +130,7 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
       *reinterpret_cast<uint4*>(y + ((size_t)img * kPix0 + p) * kC0 + cg * 8) = pack8(o);
     }
   }
-  if (partials == nullptr) return;
+  if (partials == nullptr && accum == nullptr) return;
   // fold the 32 threads sharing a channel group: 4 lanes per warp (xor 8, 16), then 8 warps via smem
   if (threadIdx.x < 2 * kC0) (&s_red[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
@@ -145,7 +145,10 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
     }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * kC0) partials[(size_t)blockIdx.x * 2 * kC0 + threadIdx.x] = (&s_red[0][0])[threadIdx.x];
+  if (threadIdx.x < 2 * kC0) {
+    if (accum != nullptr) atomicAdd(accum + threadIdx.x, (double)(&s_red[0][0])[threadIdx.x]);
+    else partials[(size_t)blockIdx.x * 2 * kC0 + threadIdx.x] = (&s_red[0][0])[threadIdx.x];
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -286,15 +289,54 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+// Fused statistics (BnFusedFwd): the first C/8 threads of every CTA turn the fp64 accumulators into scale / shift for
+// 8 channels each (shared memory, read by everyone after the barrier); CTA 0 also publishes scale / shift / mean /
+// invstd for the backward pass and updates the running statistics (momentum, unbiased variance) and the step counter.
+__device__ __forceinline__ void fused_fwd_coeffs(const BnFusedFwd& st, int c, float* s_sc, float* s_sh) {
+  const int cv = c >> 3;
+  if ((int)threadIdx.x < cv) {
+    const bool publish = blockIdx.x == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = threadIdx.x * 8 + j;
+      // fp64 only where cancellation matters (E[x^2] - mean^2); one multiply and one fma, no division, no sqrt
+      const double mean = st.accum[ch] * st.inv_count;
+      const float var = fmaxf((float)fma(st.accum[c + ch], st.inv_count, -mean * mean), 0.f);
+      const float invstd = rsqrtf(var + st.eps);
+      const float sc = st.gamma[ch] * invstd;
+      const float sh = st.beta[ch] - (float)mean * sc;
+      s_sc[ch] = sc;
+      s_sh[ch] = sh;
+      if (publish) {
+        st.out.scale[ch] = sc;
+        st.out.shift[ch] = sh;
+        st.out.mean[ch] = (float)mean;
+        st.out.invstd[ch] = invstd;
+        if (st.running_mean != nullptr) {
+          st.running_mean[ch] = (1.f - st.momentum) * st.running_mean[ch] + st.momentum * (float)mean;
+          st.running_var[ch] = (1.f - st.momentum) * st.running_var[ch] + st.momentum * (var * st.unbias);
+        }
+      }
+    }
+    if (publish && threadIdx.x == 0 && st.num_batches_tracked != nullptr) *st.num_batches_tracked += 1;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void load8s(const float* p, float (&f)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = p[j];
+}
+
 // a = relu(y*scale+shift) [+ 2x2 max-pool]; a thread owns one 8-channel group and walks output pixels; the raw
 // loads of U pixels are issued before any arithmetic (these passes are latency-, not bandwidth-limited otherwise).
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
-                    uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
+                    uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale, const BnFusedFwd st) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
+  __shared__ float s_sc[512], s_sh[512];
   constexpr int U = POOL ? 2 : 4;
   const int cv = c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
@@ -302,8 +344,14 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
   const unsigned total = (unsigned)n * oh * ow;
   const unsigned stride = gridDim.x * rows_per_blk;
   float sc[8], sh[8];
-  load8f(scale + v * 8, sc);
-  load8f(shift + v * 8, sh);
+  if (st.accum != nullptr) {
+    fused_fwd_coeffs(st, c, s_sc, s_sh);
+    load8s(s_sc + v * 8, sc);
+    load8s(s_sh + v * 8, sh);
+  } else {
+    load8f(scale + v * 8, sc);
+    load8f(shift + v * 8, sh);
+  }
   for (unsigned pix0 = blockIdx.x * rows_per_blk + lane_row; pix0 < total; pix0 += U * stride) {
     uint4 raw[U][POOL ? 4 : 1];
 #pragma unroll
@@ -358,18 +406,21 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
 __global__ void __launch_bounds__(kThreads)
 bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                             const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c,
-                            uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale) {
+                            uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale, const BnFusedFwd st) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ __nv_bfloat16 s_t[];                  // [c][ppix + 2] (padded)
+  __shared__ float s_sc[512], s_sh[512];
+  const bool fused = st.accum != nullptr;
+  if (fused) fused_fwd_coeffs(st, c, s_sc, s_sh);
   const int oh = h >> 1, ow = w >> 1, ppix = oh * ow, cv = c >> 3, ld = ppix + 2;
   const long long img = blockIdx.x;
   for (int i = threadIdx.x; i < ppix * cv; i += kThreads) {
     const int v = i % cv, pp = i / cv;
     const int ph = pp / ow, pw = pp - ph * ow;
     float sc[8], sh[8], r[8];
-    load8f(scale + v * 8, sc);
-    load8f(shift + v * 8, sh);
+    if (fused) { load8s(s_sc + v * 8, sc); load8s(s_sh + v * 8, sh); }
+    else { load8f(scale + v * 8, sc); load8f(shift + v * 8, sh); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) r[k] = 0.f;
     const __nv_bfloat16* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
@@ -485,7 +536,7 @@ __device__ __forceinline__ uint4 load_g_packed(const BwdCtx& k, int img, int ph,
 
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2)
-bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
+bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials, double* __restrict__ accum) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ float s_part[];                       // [2][c]
@@ -604,7 +655,11 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials) {
     atomicAdd(&s_part[k.c + v * 8 + j], s_dzx[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) partials[(size_t)blockIdx.x * 2 * k.c + i] = s_part[i];
+  if (accum != nullptr) {
+    for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) atomicAdd(accum + i, (double)s_part[i]);
+  } else {
+    for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) partials[(size_t)blockIdx.x * 2 * k.c + i] = s_part[i];
+  }
 }
 
 __global__ void __launch_bounds__(32 * kFinGroups)
@@ -659,10 +714,11 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
 template <bool POOL, bool HAS_DB>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
-                    float* __restrict__ dbias) {
+                    float* __restrict__ dbias, const BnFusedBwd fb) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   extern __shared__ float s_db[];                          // [c]
+  __shared__ float s_c1[512], s_k0[512], s_k1[512];
   const int cv = k.c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
   const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
@@ -670,6 +726,30 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
   // dy = c1 * (dz - c2 - xhat * c3), xhat = (y - mean) * invstd   ==>   dy = c1 * dz + k0 - k1 * y
   float sc[8], sh[8], c1[8], k0[8], k1[8], db[8];
   load8f(k.scale + v * 8, sc); load8f(k.shift + v * 8, sh);
+  if (fb.accum != nullptr) {
+    // fused statistics: sum dz and sum dz*y arrive as fp64 accumulators; the first C/8 threads derive the three
+    // per-channel constants (shared memory) and CTA 0 writes dgamma = sum dz*xhat and dbeta = sum dz
+    if ((int)threadIdx.x < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = threadIdx.x * 8 + j;
+        const double a = fb.accum[ch];
+        const double is = (double)k.invstd[ch], mu = (double)k.mean[ch];
+        const double b = is * (fb.accum[k.c + ch] - mu * a);           // sum(dz * y) -> sum(dz * xhat)
+        const float cc1 = fb.gamma[ch] * k.invstd[ch];
+        const float cc2 = (float)(a * fb.inv_count), cc3 = (float)(b * fb.inv_count);
+        const float kk1 = cc1 * k.invstd[ch] * cc3;
+        s_c1[ch] = cc1;
+        s_k1[ch] = kk1;
+        s_k0[ch] = fmaf(kk1, k.mean[ch], -cc1 * cc2);
+        if (blockIdx.x == 0) { fb.dbeta[ch] = (float)a; fb.dgamma[ch] = (float)b; }
+      }
+    }
+    __syncthreads();
+    load8s(s_c1 + v * 8, c1); load8s(s_k0 + v * 8, k0); load8s(s_k1 + v * 8, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) db[j] = 0.f;
+  } else {
   load8f(coef + v * 8, c1);
   {
     float mu[8], is[8], c2[8], c3[8];
@@ -681,6 +761,7 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
       k0[j] = fmaf(k1[j], mu[j], -c1[j] * c2[j]);
       db[j] = 0.f;
     }
+  }
   }
   const long long stride = (long long)gridDim.x * rows_per_blk;
   if constexpr (POOL) {
@@ -953,9 +1034,9 @@ head_kernel(HeadArgs a) {
 int conv0_partial_rows() { return sm_count() * 2; }
 
 int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const float* bias, __nv_bfloat16* y,
-                     float* stat_partials, int batch, cudaStream_t s) {
+                     float* stat_partials, double* stat_accum, int batch, cudaStream_t s) {
   const int grid = batch < conv0_partial_rows() ? batch : conv0_partial_rows();
-  launch_pdl(conv0_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, weight, bias, y, stat_partials, batch);
+  launch_pdl(conv0_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, weight, bias, y, stat_partials, stat_accum, batch);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return grid;
 }
@@ -990,21 +1071,22 @@ static void check_channels(int c) {
 
 void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
                          int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
-                         cudaStream_t s) {
+                         const BnFusedFwd& fused, cudaStream_t s) {
   check_channels(c);
+  if (fused.accum != nullptr && c > 512) throw std::runtime_error("fused BatchNorm statistics support C <= 512");
   if (pool && ((h | w) & 1)) throw std::runtime_error("2x2 max-pool needs even H and W");
   if (flatten_chw) {
     if (!pool) throw std::runtime_error("flatten_chw is only implemented together with the pool");
     const int ppix = (h / 2) * (w / 2);
     const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
-    launch_pdl(bn_relu_pool_flatten_kernel, dim3(n), dim3(kThreads), smem, s, y, scale, shift, out, h, w, c, q_out, q_scale);
+    launch_pdl(bn_relu_pool_flatten_kernel, dim3(n), dim3(kThreads), smem, s, y, scale, shift, out, h, w, c, q_out, q_scale, fused);
   } else {
     const long long pixels = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
     const int rows_per_blk = kThreads / (c / 8);
     const int grid = persistent_grid(pixels, rows_per_blk * (pool ? 2 : 4), 8);
     if (q_out != nullptr && (c % 32 != 0)) throw std::runtime_error("MXFP8 side output needs C % 32 == 0");
-    if (pool) launch_pdl(bn_relu_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale);
-    else launch_pdl(bn_relu_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale);
+    if (pool) launch_pdl(bn_relu_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale, fused);
+    else launch_pdl(bn_relu_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, s, y, scale, shift, out, n, h, w, c, q_out, q_scale, fused);
   }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
@@ -1012,8 +1094,8 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
 int bn_bwd_partial_rows() { return sm_count() * 4; }
 
 int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
-                         const float* mean, const float* invstd, float* partials, int n, int h, int w, int c,
-                         int pool, int g_flatten_chw, cudaStream_t s) {
+                         const float* mean, const float* invstd, float* partials, double* accum, int n, int h, int w,
+                         int c, int pool, int g_flatten_chw, cudaStream_t s) {
   check_channels(c);
   BwdCtx k{y, g, scale, shift, mean, invstd, n, h, w, c, g_flatten_chw};
   const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
@@ -1023,8 +1105,8 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   const int cap = sm_count() * 2;
   const int grid = (int)(want < cap ? want : cap);
   const size_t smem = 2 * c * sizeof(float);
-  if (pool) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, partials);
-  else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, partials);
+  if (pool) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, partials, accum);
+  else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, partials, accum);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return grid;
 }
@@ -1039,8 +1121,10 @@ void launch_bn_bwd_finalize(const float* partials, int num_partials, int channel
 
 void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
                          const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy, float* dbias,
-                         int n, int h, int w, int c, int pool, int g_flatten_chw, cudaStream_t s) {
+                         const BnFusedBwd& fused, int n, int h, int w, int c, int pool, int g_flatten_chw,
+                         cudaStream_t s) {
   check_channels(c);
+  if (fused.accum != nullptr && c > 512) throw std::runtime_error("fused BatchNorm statistics support C <= 512");
   BwdCtx k{y, g, scale, shift, mean, invstd, n, h, w, c, g_flatten_chw};
   const long long pix = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
   const int rows_per_blk = kThreads / (c / 8);
@@ -1057,11 +1141,11 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   const int grid = (int)(want < cap ? want : cap);
   const size_t smem = c * sizeof(float);
   if (dbias != nullptr) {
-    if (pool) launch_pdl(bn_bwd_apply_kernel<true, true>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
-    else launch_pdl(bn_bwd_apply_kernel<false, true>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
+    if (pool) launch_pdl(bn_bwd_apply_kernel<true, true>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias, fused);
+    else launch_pdl(bn_bwd_apply_kernel<false, true>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias, fused);
   } else {
-    if (pool) launch_pdl(bn_bwd_apply_kernel<true, false>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
-    else launch_pdl(bn_bwd_apply_kernel<false, false>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias);
+    if (pool) launch_pdl(bn_bwd_apply_kernel<true, false>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias, fused);
+    else launch_pdl(bn_bwd_apply_kernel<false, false>, dim3(grid), dim3(kThreads), smem, s, k, coef, dy, dbias, fused);
   }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }

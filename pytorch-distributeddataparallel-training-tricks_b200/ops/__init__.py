@@ -65,6 +65,14 @@ def require_native():
     return ext
 
 
+def deterministic() -> bool:
+    """``DDPT_DETERMINISTIC=1`` (or ``same_seeds(..., deterministic=True)``): every reduction of the fused step runs
+    in a fixed order -- partial rows + finalize kernels / slabs + reduction kernels instead of floating-point atomics
+    -- so two runs of the same program produce bit-identical parameters (reference: utils/customized.py:12-13,
+    ``cudnn.deterministic = True``).  Costs a few percent of step time."""
+    return os.environ.get("DDPT_DETERMINISTIC", "0") == "1"
+
+
 def attach_fused_model(model: torch.nn.Module, compute: Optional[str]) -> bool:
     """Give ``model`` its fused sm_100a forward/backward if one exists for its type."""
     from ..models import Toy_Net

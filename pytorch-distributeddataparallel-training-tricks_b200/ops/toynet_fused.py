@@ -62,8 +62,14 @@ class _Workspace:
                    e(batch, 512)]
         self.da3_hwc = e(batch, 4, 4, 512)                 # da[3] (flatten order c,h,w) as channels-last
         self.saved_x: Optional[torch.Tensor] = None
+        # fused BatchNorm statistics: fp64 accumulators [10][2][512] (rows 0-4 forward sum / sum of squares per layer,
+        # rows 5-9 backward sum dz / sum dz*y), cleared once per training step
+        self.stat = torch.zeros(10, 2 * 512, dtype=torch.float64, device=device)
         # block-scaled fp8 copies of the activations feeding conv.7, conv.10 and dense.1 ("O1-fp8")
         self.q = {}
+
+    def acc(self, row: int, channels: int) -> torch.Tensor:
+        return self.stat[row, : 2 * channels]
 
     def fp8_buffers(self, k: int, like: torch.Tensor):
         if k not in self.q:
@@ -88,12 +94,25 @@ class FusedToyNet:
         self._w_fp8: Dict[int, tuple] = {}
         self._staging: Optional[torch.Tensor] = None
         self.launches = 0
+        import os
+        # BatchNorm statistics travel as partial rows folded by *_finalize kernels (ordered, bit-stable).  The alternative
+        # (DDPT_FUSED_BN_STATS=1) lets the producing kernels' epilogues add into fp64 accumulators and the consuming pass
+        # derive the coefficients itself -- ten launches fewer.  Measured on the same box (200 steps, graph + PDL):
+        # 1.485 ms fused vs 1.472 ms with the finalize kernels: under programmatic dependent launch a finalize kernel
+        # costs ~4 us, about what the contended red.global.add.f64 tail of 148 CTAs plus the consumers' prologue costs.
+        # The fused path therefore stays opt-in (it is also unordered, i.e. not bit-reproducible).
+        from . import deterministic
+        self.fused_stats = (compute != "fp8" and not deterministic()
+                            and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
 
     def count_launches(self, batch: int) -> int:
         """Kernels of ours in one training step (forward + backward + unscale + scale update + optimizer)."""
         fwd = 1 + 1 + 1 + 3 * 3 + 3              # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio (head: in bwd)
         bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
         bwd += 1 + 2                             # flatten -> channels-last transpose | split-K slab reductions (conv.3, conv.10 wgrad)
+        if self.fused_stats:
+            fwd -= 5                             # no bn_finalize launches
+            bwd -= 5                             # no bn_bwd_finalize launches
         return fwd + bwd + 3                     # + unscale, scale update, optimizer (profiles/launches_step_b1024_v9.txt)
 
     # -- helpers ------------------------------------------------------------------------------------
@@ -162,6 +181,18 @@ class FusedToyNet:
         else:
             self.ext.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, _EPS, ws.coef[k])
 
+    def _bn_act(self, k: int, ws: _Workspace, train: bool, fused: bool, rows: int, count: float, pool: bool,
+                flatten: bool, q) -> None:
+        """BatchNorm (batch or running statistics) + ReLU (+ 2x2 max-pool, + flatten) of block k: y[k] -> a[k]."""
+        ext, bn = self.ext, self.bn[k]
+        if fused:      # the pass derives scale/shift from the accumulators itself and publishes coef / running stats
+            ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, flatten, q[0], q[1], ws.acc(k, bn.num_features), count,
+                             bn.weight, bn.bias, _EPS, _MOMENTUM, bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked)
+        else:
+            self._bn_coeffs(k, ws, train, rows, count)
+            ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, flatten, q[0], q[1])
+
     def forward_impl(self, x: torch.Tensor, train: bool, target: Optional[torch.Tensor] = None,
                      metrics: Optional[torch.Tensor] = None, head: bool = True) -> torch.Tensor:
         ext, P = self.ext, self.params
@@ -175,10 +206,13 @@ class FusedToyNet:
         ws = self.workspace(batch)
         ws.saved_x = x
         part = ws.part if train else None
+        fused = train and self.fused_stats
+        if fused:
+            ws.stat.zero_()                                    # all ten accumulator rows (forward and backward)
+        stat_out = (lambda k, c: ws.acc(k, c)) if fused else (lambda k, c: part)
         # block 0: direct conv + BN + ReLU
-        rows = ext.conv0_fwd(x, P[0].detach().reshape(64, 9).contiguous(), P[1].detach(), ws.y[0], part)
-        self._bn_coeffs(0, ws, train, rows, batch * 676.0)
-        ext.bn_relu_pool(ws.y[0], ws.coef[0], ws.a[0], False, False, None, None)
+        rows = ext.conv0_fwd(x, P[0].detach().reshape(64, 9).contiguous(), P[1].detach(), ws.y[0], stat_out(0, 64))
+        self._bn_act(0, ws, train, fused, rows, batch * 676.0, False, False, (None, None))
         # blocks 1..3: tcgen05 implicit GEMM + BN + ReLU (+pool)
         act = ws.a[0]
         for k, (pidx, h_in, c_in, c_out, pool) in enumerate(_TC_BLOCKS, start=1):
@@ -188,10 +222,10 @@ class FusedToyNet:
                 wq, wsc = self._weight_fp8(pidx)
                 _, tiles = gemm.conv_fwd_mxfp8(xq, xs, wq, wsc, 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
             else:
-                _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
-            self._bn_coeffs(k, ws, train, 4 * tiles, batch * float(h_out * h_out))
+                _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False,
+                                         stat_out(k, c_out), ws.y[k])
             q = ws.fp8_buffers(k + 1, ws.a[k]) if self.compute == "fp8" else (None, None)   # consumer: conv.7 / conv.10 / dense.1
-            ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, k == 3, q[0], q[1])
+            self._bn_act(k, ws, train, fused, 4 * tiles, batch * float(h_out * h_out), pool, k == 3, q)
             act = ws.a[k]
         # dense.1 + BN1d + ReLU
         y4 = ws.y[4].view(batch, 512)
@@ -201,9 +235,8 @@ class FusedToyNet:
             _, tiles = gemm.linear_fwd_mxfp8(xq, xs, wq, wsc, P[17].detach(), False, part, y4)
         else:
             _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(),
-                                     False, part, y4.view(1, 1, batch, 512), block_n=64)
-        self._bn_coeffs(4, ws, train, 4 * tiles, float(batch))
-        ext.bn_relu_pool(ws.y[4], ws.coef[4], ws.a[4], False, False, None, None)
+                                     False, stat_out(4, 512), y4.view(1, 1, batch, 512), block_n=64)
+        self._bn_act(4, ws, train, fused, 4 * tiles, float(batch), False, False, (None, None))
         if not head:       # training step engine: the backward head launch also produces loss / accuracy
             return ws.logits
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)
@@ -277,12 +310,18 @@ class FusedToyNet:
                      dbias_idx: Optional[int]) -> None:
         ext, bn = self.ext, self.bn[k]
         gamma_idx = {0: 2, 1: 6, 2: 10, 3: 14, 4: 18}[k]
+        dy = ws.dy[k] if k < 4 else ws.dy[4].view(ws.batch, 1, 1, 512)
+        dbias = grads[dbias_idx] if dbias_idx is not None else None
+        if self.fused_stats:
+            acc = ws.acc(5 + k, bn.num_features)             # cleared with the forward accumulators at the start of the step
+            ext.bn_bwd_reduce(ws.y[k], g, ws.coef[k], acc, pool, flatten)
+            ext.bn_bwd_apply(ws.y[k], g, ws.coef[k], ws.bcoef[k], dy, dbias, pool, flatten, acc, count, bn.weight,
+                             grads[gamma_idx], grads[gamma_idx + 1])
+            return
         rows = ext.bn_bwd_reduce(ws.y[k], g, ws.coef[k], ws.part, pool, flatten)
         ext.bn_bwd_finalize(ws.part, rows, count, bn.weight, ws.coef[k], grads[gamma_idx], grads[gamma_idx + 1],
                             ws.bcoef[k], False)
-        dy = ws.dy[k] if k < 4 else ws.dy[4].view(ws.batch, 1, 1, 512)
-        ext.bn_bwd_apply(ws.y[k], g, ws.coef[k], ws.bcoef[k], dy, grads[dbias_idx] if dbias_idx is not None else None,
-                         pool, flatten)
+        ext.bn_bwd_apply(ws.y[k], g, ws.coef[k], ws.bcoef[k], dy, dbias, pool, flatten)
 
     # -- autograd entry ------------------------------------------------------------------------------------
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
