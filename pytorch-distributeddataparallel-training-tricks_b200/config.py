@@ -69,6 +69,8 @@ def build_parser() -> argparse.ArgumentParser:
                      help="keep stepping the warm-up scheduler after warm-up so the cosine decay runs (reference quirk Q2 off)")
     ext.add_argument("--save_resume", action="store_true",
                      help="write a full-state {exp_name}.resume.pt every epoch")
+    ext.add_argument("--deterministic", action="store_true",
+                     help="bit-reproducible runs: ordered reductions instead of float atomics in the fused kernels")
     ext.add_argument("--no_graph", action="store_true", help="disable CUDA-graph capture of the step")
     ext.add_argument("--profile", action="store_true", help="emit NVTX ranges and step timing summary")
     ext.add_argument("--quiet", action="store_true", help="only rank 0 prints epoch lines; no progress bars")

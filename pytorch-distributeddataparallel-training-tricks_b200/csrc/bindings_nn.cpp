@@ -41,14 +41,20 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
                                 bias.data_ptr<float>(), bfm(y), part, accum, batch, cur());
 }
 
-void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db) {
+void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10::optional<at::Tensor> partials) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
   need(dy, at::kBFloat16, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
   const int batch = (int)(x.numel() / (28 * 28));
   TORCH_CHECK(dy.numel() == (int64_t)batch * 26 * 26 * 64 && dw.numel() == 576 && db.numel() == 64);
   c10::cuda::CUDAGuard g(x.device());
+  float* part = nullptr;
+  if (partials.has_value()) {
+    need(*partials, at::kFloat, "partials");
+    TORCH_CHECK(partials->numel() >= (int64_t)ddpt::conv0_wgrad_partial_rows() * 640, "conv0_wgrad: partials too small");
+    part = partials->data_ptr<float>();
+  }
   ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
-                           db.data_ptr<float>(), batch, cur());
+                           db.data_ptr<float>(), part, batch, cur());
 }
 
 // coeffs: float [4][C] = scale, shift, mean, invstd
@@ -193,7 +199,7 @@ void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor b
 void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> target, c10::optional<at::Tensor> logits,
           c10::optional<at::Tensor> metrics, c10::optional<at::Tensor> loss_scale, c10::optional<at::Tensor> da,
           c10::optional<at::Tensor> dw, c10::optional<at::Tensor> db, c10::optional<at::Tensor> dlogits,
-          double extra_div) {
+          double extra_div, c10::optional<at::Tensor> partials) {
   need(a, at::kBFloat16, "a"); need(w, at::kFloat, "w"); need(b, at::kFloat, "b");
   TORCH_CHECK(a.dim() == 2 && a.size(1) == 512 && w.numel() == 5120 && b.numel() == 10);
   c10::cuda::CUDAGuard guard(a.device());
@@ -213,6 +219,12 @@ void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> ta
   TORCH_CHECK(h.target != nullptr || (h.metrics == nullptr && (h.da == nullptr || h.dlogits != nullptr)),
               "head: target is required for metrics / fused cross-entropy gradient");
   h.extra_div = (float)extra_div;
+  if (partials.has_value()) {
+    need(*partials, at::kFloat, "partials");
+    TORCH_CHECK(partials->numel() >= (int64_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * ddpt::head_partial_cols(),
+                "head: partials too small");
+    h.partials = partials->data_ptr<float>();
+  }
   ddpt::launch_head(h, cur());
 }
 
@@ -274,7 +286,11 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("conv0_partial_rows", &conv0_partial_rows);
   m.def("bn_bwd_partial_rows", &bn_bwd_partial_rows);
   m.def("conv0_fwd", &conv0_fwd);
-  m.def("conv0_wgrad", &conv0_wgrad);
+  m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none());
+  m.def("det_workspace_floats", []() {     // fp32 elements of the deterministic-mode partial-row workspace
+    return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,
+                                      (int64_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * ddpt::head_partial_cols());
+  });
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_eval_coeffs", &bn_eval_coeffs);
   m.def("bn_relu_pool", &bn_relu_pool, py::arg("y"), py::arg("coeffs"), py::arg("out"), py::arg("pool"),
@@ -288,5 +304,7 @@ void ddpt_bind_nn(pybind11::module_& m) {
         py::arg("dbias"), py::arg("pool"), py::arg("flatten_chw"), py::arg("accum") = py::none(), py::arg("count") = 0.0,
         py::arg("gamma") = py::none(), py::arg("dgamma") = py::none(), py::arg("dbeta") = py::none());
   m.def("chw_to_hwc", &chw_to_hwc);
-  m.def("head", &head);
+  m.def("head", &head, py::arg("a"), py::arg("w"), py::arg("b"), py::arg("target"), py::arg("logits"), py::arg("metrics"),
+        py::arg("loss_scale"), py::arg("da"), py::arg("dw"), py::arg("db"), py::arg("dlogits"), py::arg("extra_div"),
+        py::arg("partials") = py::none());
 }

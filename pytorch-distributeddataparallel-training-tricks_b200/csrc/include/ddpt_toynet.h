@@ -18,8 +18,11 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/
                      __nv_bfloat16* y, float* stat_partials /*[rows][2][64] or null*/, double* stat_accum,
                      int batch, cudaStream_t s);
 // dW [64][9], db [64] accumulated with atomics into zero-initialised (or beta=1) fp32 buffers.
-void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
-                        cudaStream_t s);
+// partials (optional, [conv0_wgrad_partial_rows()][640] fp32): deterministic mode -- every block writes one row and an
+// ordered reduction kernel folds them into dw / db instead of global float atomics.
+int conv0_wgrad_partial_rows();
+void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
+                        int batch, cudaStream_t s);
 
 // ---- BatchNorm (training) ---------------------------------------------------------------------------
 struct BnCoeffs {          // all float [C]
@@ -102,7 +105,10 @@ struct HeadArgs {
   float* db;                   // [10]     += sum dlogits
   const float* dlogits;        // optional [B,10]: externally supplied d(loss)/d(logits) (autograd path)
   float extra_div;             // Q1: additional division of the loss by B (1/B) -> pass (float)B, or 1
+  float* partials;             // optional [#SMs][head_partial_cols()]: deterministic mode (ordered cross-block fold of
+                               // dw / db / metrics instead of global float atomics)
 };
+int head_partial_cols();
 void launch_head(const HeadArgs& args, cudaStream_t s);
 
 }  // namespace ddpt

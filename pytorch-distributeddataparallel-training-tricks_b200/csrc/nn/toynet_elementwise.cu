@@ -96,7 +96,7 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
-  __shared__ float s_red[2][kC0];
+  __shared__ float s_red[kThreads / 32][2][kC0];            // one slot per warp: the block fold runs in a fixed order
   const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
   float wr[8][9], br[8], acc_s[8], acc_q[8];
 #pragma unroll
@@ -131,33 +131,35 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
     }
   }
   if (partials == nullptr && accum == nullptr) return;
-  // fold the 32 threads sharing a channel group: 4 lanes per warp (xor 8, 16), then 8 warps via smem
-  if (threadIdx.x < 2 * kC0) (&s_red[0][0])[threadIdx.x] = 0.f;
-  __syncthreads();
+  // fold the 32 threads sharing a channel group: 4 lanes per warp (xor 8, 16), then the 8 warps in warp order
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     float s = acc_s[c], q = acc_q[c];
     s += __shfl_xor_sync(0xffffffffu, s, 8);  q += __shfl_xor_sync(0xffffffffu, q, 8);
     s += __shfl_xor_sync(0xffffffffu, s, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
     if ((threadIdx.x & 31) < 8) {
-      atomicAdd(&s_red[0][cg * 8 + c], s);
-      atomicAdd(&s_red[1][cg * 8 + c], q);
+      s_red[warp][0][cg * 8 + c] = s;
+      s_red[warp][1][cg * 8 + c] = q;
     }
   }
   __syncthreads();
   if (threadIdx.x < 2 * kC0) {
-    if (accum != nullptr) atomicAdd(accum + threadIdx.x, (double)(&s_red[0][0])[threadIdx.x]);
-    else partials[(size_t)blockIdx.x * 2 * kC0 + threadIdx.x] = (&s_red[0][0])[threadIdx.x];
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) tot += (&s_red[w][0][0])[threadIdx.x];
+    if (accum != nullptr) atomicAdd(accum + threadIdx.x, (double)tot);
+    else partials[(size_t)blockIdx.x * 2 * kC0 + threadIdx.x] = tot;
   }
 }
 
 __global__ void __launch_bounds__(kThreads)
 conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16* __restrict__ dy,
-                   float* __restrict__ dw, float* __restrict__ db, int batch) {
+                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ partials, int batch) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
-  __shared__ float s_acc[kC0 * 10];
+  __shared__ float s_acc[kThreads / 32][kC0 * 10];         // one slot per warp: ordered block fold
   const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
   float acc[8][10];
 #pragma unroll
@@ -197,8 +199,7 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
       }
     }
   }
-  for (int i = threadIdx.x; i < kC0 * 10; i += kThreads) s_acc[i] = 0.f;
-  __syncthreads();
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -206,14 +207,43 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
       float v = acc[c][t];
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(cg * 8 + c) * 10 + t], v);
+      if ((threadIdx.x & 31) < 8) s_acc[warp][(cg * 8 + c) * 10 + t] = v;
     }
   __syncthreads();
   for (int i = threadIdx.x; i < kC0 * 10; i += kThreads) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) tot += s_acc[w][i];
     const int ch = i / 10, t = i - ch * 10;
-    if (t < 9) atomicAdd(dw + ch * 9 + t, s_acc[i]);
-    else atomicAdd(db + ch, s_acc[i]);
+    if (partials != nullptr) {
+      // deterministic mode: one row per block ([576 dw | 64 db]), folded in block order by reduce_rows_kernel
+      partials[(size_t)blockIdx.x * (kC0 * 10) + (t < 9 ? ch * 9 + t : kC0 * 9 + ch)] = tot;
+    } else if (t < 9) {
+      atomicAdd(dw + ch * 9 + t, tot);
+    } else {
+      atomicAdd(db + ch, tot);
+    }
   }
+}
+
+// out[i] (+)= sum over rows r (in order) of partials[r * ld + i]: the ordered cross-block fold of deterministic mode
+__global__ void __launch_bounds__(kThreads)
+reduce_rows_kernel(const float* __restrict__ partials, int rows, int ld, int n, float* __restrict__ out, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;             // fixed association: four interleaved chains, then a tree
+  int r = 0;
+  for (; r + 3 < rows; r += 4) {
+    a0 += partials[(size_t)r * ld + i];
+    a1 += partials[(size_t)(r + 1) * ld + i];
+    a2 += partials[(size_t)(r + 2) * ld + i];
+    a3 += partials[(size_t)(r + 3) * ld + i];
+  }
+  for (; r < rows; ++r) a0 += partials[(size_t)r * ld + i];
+  const float tot = (a0 + a1) + (a2 + a3);
+  out[i] = accumulate ? out[i] + tot : tot;
 }
 
 // ================================================================================================
@@ -539,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials, double* __restrict__ accum) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
-  extern __shared__ float s_part[];                       // [2][c]
+  extern __shared__ float s_part[];                       // [rows_per_blk][2][c]: ordered block fold (no float atomics)
   const int cv = k.c >> 3;
   const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kThreads / cv;
   const int oh = POOL ? k.h >> 1 : k.h, ow = POOL ? k.w >> 1 : k.w;
@@ -647,18 +677,20 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials, double* __restrict_
       }
     }
   }
-  for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) s_part[i] = 0.f;
-  __syncthreads();
+  {
+    float* mine = s_part + (size_t)lane_row * 2 * k.c;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&s_part[v * 8 + j], s_dz[j]);
-    atomicAdd(&s_part[k.c + v * 8 + j], s_dzx[j]);
+    for (int j = 0; j < 8; ++j) {
+      mine[v * 8 + j] = s_dz[j];
+      mine[k.c + v * 8 + j] = s_dzx[j];
+    }
   }
   __syncthreads();
-  if (accum != nullptr) {
-    for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) atomicAdd(accum + i, (double)s_part[i]);
-  } else {
-    for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) partials[(size_t)blockIdx.x * 2 * k.c + i] = s_part[i];
+  for (int i = threadIdx.x; i < 2 * k.c; i += kThreads) {
+    float tot = 0.f;
+    for (int r = 0; r < rows_per_blk; ++r) tot += s_part[(size_t)r * 2 * k.c + i];
+    if (accum != nullptr) atomicAdd(accum + i, (double)tot);
+    else partials[(size_t)blockIdx.x * 2 * k.c + i] = tot;
   }
 }
 
@@ -928,6 +960,7 @@ chw_to_hwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
 // Head: Linear(512,10) + CE(mean)/B + argmax (+ backward)
 // ================================================================================================
 constexpr int kFeat = 512, kCls = 10, kHeadRows = 8;   // one warp per row, 8 rows per block iteration
+constexpr int kHeadPartialCols = kCls * kFeat + kCls + 2;
 
 __global__ void __launch_bounds__(kThreads)
 head_kernel(HeadArgs a) {
@@ -949,9 +982,13 @@ head_kernel(HeadArgs a) {
   const float inv_b = 1.0f / (float)a.batch;
   const float gscale = train ? (a.loss_scale ? *a.loss_scale : 1.0f) * inv_b / a.extra_div : 0.f;
   float my_loss = 0.f, my_correct = 0.f;
-  for (int row = blockIdx.x * kHeadRows + warp; row < a.batch; row += gridDim.x * kHeadRows) {
+  // uniform trip count (the ordered weight-gradient fold below synchronises the block every iteration)
+  for (int base = blockIdx.x * kHeadRows; base < a.batch; base += gridDim.x * kHeadRows) {
+    const int row = base + warp;
+    const bool active = row < a.batch;
+    float dl[kCls], x[16];
+    if (active) {
     // lane owns features {64*j + 2*lane + e : j < 8, e < 2}: 4-byte coalesced loads, conflict-light smem
-    float x[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(a.a + (size_t)row * kFeat + 64 * j + 2 * lane);
@@ -989,7 +1026,6 @@ head_kernel(HeadArgs a) {
       }
     }
     if (train) {
-      float dl[kCls];
       const float inv_den = 1.0f / den;
 #pragma unroll
       for (int k = 0; k < kCls; ++k)
@@ -1001,25 +1037,52 @@ head_kernel(HeadArgs a) {
 #pragma unroll
       for (int k = 0; k < kCls; ++k) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int f = 64 * (j >> 1) + 2 * lane + (j & 1);
-          dx[j] = fmaf(dl[k], s_w[k][f], dx[j]);
-          atomicAdd(&s_dw[k][f], dl[k] * x[j]);
-        }
-        if (lane == 0) atomicAdd(&s_db[k], dl[k]);
+        for (int j = 0; j < 16; ++j) dx[j] = fmaf(dl[k], s_w[k][64 * (j >> 1) + 2 * lane + (j & 1)], dx[j]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint32_t*>(a.da + (size_t)row * kFeat + 64 * j + 2 * lane) = pack_bf16x2(dx[2 * j], dx[2 * j + 1]);
     }
+    }  // active
+    if (train) {
+      // dW += dlogits^T x, one warp (= one row) at a time in warp order: lanes own disjoint features, so these are
+      // plain read-modify-writes and the sum over rows has a fixed association (no shared-memory float atomics)
+      for (int w = 0; w < kHeadRows; ++w) {
+        if (warp == w && active) {
+#pragma unroll
+          for (int k = 0; k < kCls; ++k) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s_dw[k][64 * (j >> 1) + 2 * lane + (j & 1)] += dl[k] * x[j];
+            if (lane == 0) s_db[k] += dl[k];
+          }
+        }
+        __syncthreads();
+      }
+    }
   }
-  if (lane == 0) {
-    atomicAdd(&s_metric[0], my_loss);
-    atomicAdd(&s_metric[1], my_correct);
+  __shared__ float s_m[kHeadRows][2];
+  if (lane == 0) { s_m[warp][0] = my_loss; s_m[warp][1] = my_correct; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, c = 0.f;
+#pragma unroll
+    for (int w = 0; w < kHeadRows; ++w) { l += s_m[w][0]; c += s_m[w][1]; }
+    s_metric[0] = l * inv_b / a.extra_div * (float)a.batch;             // batch_loss * B
+    s_metric[1] = c;
   }
   __syncthreads();
+  if (a.partials != nullptr) {
+    // deterministic mode: one row per block [5120 dW | 10 db | 2 metrics]; reduce_rows_kernel folds them in block order
+    float* row = a.partials + (size_t)blockIdx.x * kHeadPartialCols;
+    if (train) {
+      for (int i = threadIdx.x; i < kCls * kFeat; i += kThreads) row[i] = (&s_dw[0][0])[i];
+      if (threadIdx.x < kCls) row[kCls * kFeat + threadIdx.x] = s_db[threadIdx.x];
+    }
+    if (threadIdx.x < 2) row[kCls * kFeat + kCls + threadIdx.x] = s_metric[threadIdx.x];
+    return;
+  }
   if (threadIdx.x == 0 && a.metrics != nullptr) {
-    atomicAdd(a.metrics, s_metric[0] * inv_b / a.extra_div * (float)a.batch);   // += batch_loss * B
+    atomicAdd(a.metrics, s_metric[0]);
     atomicAdd(a.metrics + 1, s_metric[1]);
   }
   if (train) {
@@ -1041,10 +1104,17 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const floa
   return grid;
 }
 
-void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, int batch,
-                        cudaStream_t s) {
+int conv0_wgrad_partial_rows() { return sm_count() * 2; }
+
+void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
+                        int batch, cudaStream_t s) {
   const int grid = batch < sm_count() * 2 ? batch : sm_count() * 2;
-  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, batch);
+  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, partials, batch);
+  if (partials != nullptr) {          // deterministic mode: fold the block rows in order (dw: 576 columns, db: 64)
+    launch_pdl(reduce_rows_kernel, dim3((kC0 * 9 + kThreads - 1) / kThreads), dim3(kThreads), 0, s,
+               (const float*)partials, grid, kC0 * 10, kC0 * 9, dw, 1);
+    launch_pdl(reduce_rows_kernel, dim3(1), dim3(kThreads), 0, s, (const float*)(partials + kC0 * 9), grid, kC0 * 10, kC0, db, 1);
+  }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1104,7 +1174,7 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   // one resident wave (2 CTAs per SM at 128 registers): half the partial rows for bn_bwd_finalize to fold
   const int cap = sm_count() * 2;
   const int grid = (int)(want < cap ? want : cap);
-  const size_t smem = 2 * c * sizeof(float);
+  const size_t smem = (size_t)rows_per_blk * 2 * c * sizeof(float);       // 16 KiB for any C
   if (pool) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, k, partials, accum);
   else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, k, partials, accum);
   DDPT_CUDA_CHECK(cudaGetLastError());
@@ -1150,11 +1220,24 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
+int head_partial_cols() { return kHeadPartialCols; }
+
 void launch_head(const HeadArgs& args, cudaStream_t s) {
   int grid = (args.batch + kHeadRows - 1) / kHeadRows;
   const int cap = sm_count();
   if (grid > cap) grid = cap;
   launch_pdl(head_kernel, dim3(grid), dim3(kThreads), 0, s, args);
+  if (args.partials != nullptr) {      // deterministic mode: ordered fold of the per-block rows
+    const float* p = args.partials;
+    if (args.da != nullptr) {
+      launch_pdl(reduce_rows_kernel, dim3((kCls * kFeat + kThreads - 1) / kThreads), dim3(kThreads), 0, s, p, grid,
+                 kHeadPartialCols, kCls * kFeat, args.dw, 1);
+      launch_pdl(reduce_rows_kernel, dim3(1), dim3(kThreads), 0, s, p + kCls * kFeat, grid, kHeadPartialCols, kCls, args.db, 1);
+    }
+    if (args.metrics != nullptr)
+      launch_pdl(reduce_rows_kernel, dim3(1), dim3(kThreads), 0, s, p + kCls * kFeat + kCls, grid, kHeadPartialCols, 2,
+                 args.metrics, 1);
+  }
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -57,7 +57,7 @@ def train(args) -> dict:
     quiet = getattr(args, "quiet", False)
 
     # ---- data (train sharded by rank, valid redundant) -----------------------------
-    same_seeds(args.seed_num)
+    same_seeds(args.seed_num, deterministic=True if getattr(args, "deterministic", False) else None)
     train_loader, valid_loader, train_sampler = make_loaders(args, device, world, rank)
     train_loader.quiet = valid_loader.quiet = quiet or not is_main and getattr(args, "quiet", False)
 

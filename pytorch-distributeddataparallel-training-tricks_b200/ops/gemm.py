@@ -250,6 +250,10 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
         block_n = 128            # measured: 128-wide accumulators beat 256 for the pixel-reduction GEMM (conv.10)
     bn = _block_n(c_in, block_n)
     mt = use_multitap(multitap)
+    from . import deterministic
+    det = deterministic()
+    if det and kh * kw > 1 and multitap is None:
+        mt = True        # split-K partials go to slabs folded in order by reduce_slabs_kernel (no red.global.add)
     if mt is None:
         # measured (profiles/kernel_probe_b1024.json): the merged wide-N kernel wins for 64-wide tiles (conv.3: 99 vs
         # 169 us) and for 128-wide tiles when the un-split grid already has >= 16 CTAs (conv.10: 124 vs 176 us); with
@@ -272,6 +276,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
         ctas = (c_out // 128) * kh * kw * (c_in // bn)
         if split_k is None:      # the stage ring fills shared memory (one CTA per SM): fill one wave, never 2.07
             split_k = max(1, min(bricks_of(box), sms // ctas))
+        if det:
+            split_k = 1          # this kernel's split-K adds with red.global (unordered): one CTA per output tile instead
     if out is None:
         out = torch.zeros((c_out, kh, kw, c_in), dtype=torch.float32, device=dy.device)
     elif not accumulate and slab is None and split_k > 1 and not out_is_zero:

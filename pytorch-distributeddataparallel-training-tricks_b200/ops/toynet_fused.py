@@ -102,6 +102,12 @@ class FusedToyNet:
         # costs ~4 us, about what the contended red.global.add.f64 tail of 148 CTAs plus the consumers' prologue costs.
         # The fused path therefore stays opt-in (it is also unordered, i.e. not bit-reproducible).
         from . import deterministic
+        # DDPT_DETERMINISTIC=1: every cross-block float reduction is an ordered fold of per-block rows (head, conv.0
+        # weight gradient) or of split-K slabs (tensor-core weight gradients) instead of red.global; with the partial-row
+        # BatchNorm statistics and the in-order block folds this makes the whole step bit-reproducible run to run
+        # (reference: utils/customized.py:12-13 sets cudnn.deterministic).
+        self.deterministic = deterministic()
+        self._det_ws: Optional[torch.Tensor] = None
         self.fused_stats = (compute != "fp8" and not deterministic()
                             and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
 
@@ -116,6 +122,14 @@ class FusedToyNet:
         return fwd + bwd + 3                     # + unscale, scale update, optimizer (profiles/launches_step_b1024_v9.txt)
 
     # -- helpers ------------------------------------------------------------------------------------
+    def det_partials(self) -> Optional[torch.Tensor]:
+        """Partial-row workspace of deterministic mode (None in fast mode)."""
+        if not self.deterministic:
+            return None
+        if self._det_ws is None:
+            self._det_ws = torch.zeros(self.ext.det_workspace_floats(), dtype=torch.float32, device=self.device)
+        return self._det_ws
+
     def workspace(self, batch: int) -> _Workspace:
         ws = self._ws.get(batch)
         if ws is None:
@@ -241,7 +255,7 @@ class FusedToyNet:
             return ws.logits
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)
         ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, ws.logits, metrics, None, None, None, None, None,
-                 float(batch))
+                 float(batch), self.det_partials() if metrics is not None else None)
         return ws.logits
 
     # -- backward --------------------------------------------------------------------------------------
@@ -273,7 +287,7 @@ class FusedToyNet:
                 fn()
 
         ext.head(ws.a[4], P[20].detach(), P[21].detach(), target, None, metrics, loss_scale, ws.da[4], grads[20],
-                 grads[21], dlogits, float(batch))
+                 grads[21], dlogits, float(batch), self.det_partials())
         ready(21); ready(20)
         # BN1d backward -> dy4
         # biases in front of a BatchNorm (dense.1, conv.3/7/10) have an identically zero gradient: their slots keep
@@ -299,7 +313,7 @@ class FusedToyNet:
             g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
         self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
         ready(3); ready(2)
-        ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1])
+        ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1], self.det_partials())
         if side_stream is not None:                       # join: everything after backward sees all weight gradients
             ev = torch.cuda.Event()
             ev.record(side_stream)

@@ -317,3 +317,42 @@ def _odd_world_buckets(rank, world):
 def test_fused_backend_on_three_gpus():
     _need_gpus(3)
     run_gpu_ranks(_odd_world_buckets, 3)
+
+
+def _engine_deterministic_world(rank, world):
+    """DDPT_DETERMINISTIC=1 at world >= 2: two runs of the same program end with bit-identical parameters (the fused
+    all-reduce sums in a fixed order: rank order in the one-shot kernel, owner order / the switch in the two-shot)."""
+    import torch.nn as nn
+    os.environ["DDPT_DETERMINISTIC"] = "1"
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    from ddpt_b200.utils import same_seeds
+    dev = torch.device("cuda", rank)
+    runs = []
+    for attempt in range(2):
+        amp.reset()
+        same_seeds(5)
+        model = Toy_Net().to(dev)
+        opt = Lookahead(SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True), k=3, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+        ddp = DDP(model, device_ids=[rank], comm="fused")
+        loss_fn = nn.CrossEntropyLoss()
+        assert ops.attach_step_engine(ddp, loss_fn, opt) and model._fused.deterministic
+        eng = ddp._ddpt_step_engine
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        ddp.train(); eng.begin_pass()
+        for step in range(12):
+            x = torch.randint(0, 256, (256, 1, 28, 28), device=dev, generator=g, dtype=torch.uint8)
+            y = (x.float().mean((1, 2, 3)) > 127.5).long() + 2 * (x[:, 0, 0, 0] > 127).long()
+            eng.run(x, y, True)
+        eng.end_pass()
+        runs.append(torch.cat([p.detach().float().reshape(-1).clone() for p in model.parameters()]))
+    assert torch.equal(runs[0].view(torch.int32), runs[1].view(torch.int32)), float((runs[0] - runs[1]).abs().max())
+    return True
+
+
+def test_deterministic_mode_world2_is_bit_reproducible():
+    _need_gpus(2)
+    run_gpu_ranks(_engine_deterministic_world, 2)

@@ -227,3 +227,44 @@ def test_chw_to_hwc_and_gemm_dispatch():
         for k, v in env.items():
             if v is not None:
                 os.environ[k] = v
+
+
+def _train_steps(steps=20, batch=256, seed=3):
+    import torch.nn as nn
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.utils import same_seeds
+    amp.reset()
+    same_seeds(seed)
+    model = Toy_Net().cuda()
+    opt = Lookahead(SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True), k=5, alpha=0.5)
+    model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+    loss_fn = nn.CrossEntropyLoss()
+    assert ops.attach_step_engine(model, loss_fn, opt)
+    eng = model._ddpt_step_engine
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    model.train(); eng.begin_pass()
+    for _ in range(steps):
+        x = torch.randint(0, 256, (batch, 1, 28, 28), device="cuda", generator=g, dtype=torch.uint8)
+        y = (x.float().mean((1, 2, 3)) > 127.5).long() + 2 * (x[:, 0, 0, 0] > 127).long()
+        eng.run(x, y, True)
+    loss_sum, correct, seen = eng.end_pass()
+    params = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).clone()
+    bufs = torch.cat([b.detach().double().reshape(-1) for b in model.buffers()]).clone()
+    amp.reset()
+    return params, bufs, loss_sum
+
+
+def test_deterministic_mode_is_bit_reproducible(monkeypatch):
+    """DDPT_DETERMINISTIC=1 (reference: cudnn.deterministic, utils/customized.py:12-13): 20 optimizer steps twice ->
+    identical parameters, BatchNorm buffers and accumulated loss, bit for bit; and the mode trains like the fast one."""
+    monkeypatch.setenv("DDPT_DETERMINISTIC", "1")
+    p1, b1, l1 = _train_steps()
+    p2, b2, l2 = _train_steps()
+    assert torch.equal(p1.view(torch.int32), p2.view(torch.int32)), float((p1 - p2).abs().max())
+    assert torch.equal(b1, b2) and l1 == l2
+    monkeypatch.setenv("DDPT_DETERMINISTIC", "0")
+    p3, b3, l3 = _train_steps()
+    assert float((p1 - p3).abs().max()) < 2e-2 * float(p1.abs().max())      # same trajectory up to rounding
+    assert l3 == pytest.approx(l1, rel=2e-2)
