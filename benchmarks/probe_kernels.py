@@ -72,6 +72,14 @@ def main():
                 t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3), flush=flush)
                 rows.append(dict(op=f"{name}.dgrad.default.skip_taps={skip}", ms=t, tflops=flops / t / 1e9))
             os.environ.pop("DDPT_DGRAD_SKIP_TAPS", None)
+            if ci == 64:
+                w_t = gemm.transpose_taps(wk, 9)
+                t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, w_t=w_t), flush=flush)
+                rows.append(dict(op=f"{name}.dgrad.pair64_kmajor", ms=t, tflops=flops / t / 1e9))
+                os.environ["DDPT_DGRAD_SKIP_TAPS"] = "0"
+                t = timeit(lambda: gemm.conv_dgrad(dy, wk, 3, 3, w_t=w_t), flush=flush)
+                rows.append(dict(op=f"{name}.dgrad.pair64_kmajor.skip_taps=0", ms=t, tflops=flops / t / 1e9))
+                os.environ.pop("DDPT_DGRAD_SKIP_TAPS", None)
             # library reference for the same layer (channels_last bf16): forward, data gradient, weight gradient
             xn = x.permute(0, 3, 1, 2)
             wn = wk.view(co, 3, 3, ci).permute(0, 3, 1, 2)

@@ -169,9 +169,10 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
   if (p.stat_partials != nullptr) {
     const int64_t tiles = (int64_t)((p.out_w + p.box_w - 1) / p.box_w) * ((p.out_h + p.box_h - 1) / p.box_h) *
                           ((p.out_n + p.box_n - 1) / p.box_n);
-    // persistent kernel: one row group per CTA (grid <= #SMs, may exceed the M-tile count when N is split)
+    // persistent kernels write one row group per CTA (grid <= #SMs); the per-tile kernel one per M tile
     const int64_t n_tiles = p.n_total / block_n;
-    const int64_t groups = std::max<int64_t>(tiles, std::min<int64_t>(tiles * n_tiles, at::cuda::getCurrentDeviceProperties()->multiProcessorCount));
+    const int64_t sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    const int64_t groups = (mode >= 1 && split_k <= 1) ? std::max<int64_t>(n_tiles, std::min<int64_t>(tiles * n_tiles, sms)) : tiles;
     TORCH_CHECK(stat_partials->numel() >= groups * 8 * p.n_total, "stat_partials too small: need ", groups * 8 * p.n_total);
     TORCH_CHECK(split_k <= 1, "statistics need the full reduction in one CTA");
   }
@@ -270,7 +271,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("update_scale", &update_scale);
   m.def("fused_lookahead_sgd", &fused_lookahead_sgd);
   m.def("cast_bf16", &cast_bf16);
-  m.def("conv_gemm", &conv_gemm);
+  m.def("conv_gemm", &conv_gemm, py::arg("a"), py::arg("b"), py::arg("out"), py::arg("out_nhw"), py::arg("box_nhw"),
+        py::arg("taps_hw"), py::arg("tap_sign"), py::arg("a_off_hw"), py::arg("b_mn_major"), py::arg("bias"),
+        py::arg("relu"), py::arg("stat_partials"), py::arg("split_k"), py::arg("block_n"), py::arg("mode"));
   m.def("wgrad_gemm", &wgrad_gemm);
   ddpt_bind_extra(m);
 }

@@ -195,6 +195,14 @@ void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor b
                             f, n, h, w, c, pool, flatten_chw, cur());
 }
 
+void transpose_taps(at::Tensor w, at::Tensor wt, int64_t taps) {
+  need(w, at::kBFloat16, "w"); need(wt, at::kBFloat16, "wt");
+  TORCH_CHECK(w.dim() == 2 && wt.dim() == 2 && w.numel() == wt.numel() && w.size(1) % taps == 0 && wt.size(1) == taps * w.size(0),
+              "transpose_taps: w [c_out, taps*c_in] -> wt [c_in, taps*c_out]");
+  c10::cuda::CUDAGuard g(w.device());
+  ddpt::launch_transpose_taps(bf(w), bfm(wt), (int)w.size(0), (int)taps, (int)(w.size(1) / taps), cur());
+}
+
 // Forward-only when da is None.  dlogits: if given, used instead of the fused cross-entropy gradient.
 void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> target, c10::optional<at::Tensor> logits,
           c10::optional<at::Tensor> metrics, c10::optional<at::Tensor> loss_scale, c10::optional<at::Tensor> da,
@@ -287,6 +295,7 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("bn_bwd_partial_rows", &bn_bwd_partial_rows);
   m.def("conv0_fwd", &conv0_fwd);
   m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none());
+  m.def("transpose_taps", &transpose_taps);
   m.def("det_workspace_floats", []() {     // fp32 elements of the deterministic-mode partial-row workspace
     return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,
                                       (int64_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * ddpt::head_partial_cols());

@@ -486,7 +486,8 @@ void launch_fused_allreduce(const AllReduceArgs& args, cudaStream_t stream) {
   } else {
     const long long vec_per_rank = args.numel / args.world / vec;
     long long want = (vec_per_rank + kThreads - 1) / kThreads;
-    int blocks = args.blocks > 0 ? args.blocks : 64;
+    // 64 CTAs of 256 threads keep ~2 MB in flight; from 1 MB per bucket up 128 CTAs pay (N = 2, 64 MB: 126 vs 168 us)
+    int blocks = args.blocks > 0 ? args.blocks : (args.numel >= (1 << 18) ? 128 : 64);
     if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
     if (want < blocks) blocks = (int)(want > 0 ? want : 1);
     const bool mc = algo == kAlgoMultimem;

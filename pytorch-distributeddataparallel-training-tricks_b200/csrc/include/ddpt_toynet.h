@@ -111,4 +111,7 @@ struct HeadArgs {
 int head_partial_cols();
 void launch_head(const HeadArgs& args, cudaStream_t s);
 
+// [c_out][taps][c_in] -> [c_in][taps][c_out] (bf16): K-major weights for the data gradient
+void launch_transpose_taps(const __nv_bfloat16* w, __nv_bfloat16* wt, int c_out, int taps, int c_in, cudaStream_t s);
+
 }  // namespace ddpt

@@ -15,6 +15,7 @@
 // roles, double-buffered TMEM accumulator, bias / ReLU / BatchNorm-statistics epilogue -- matches the
 // persistent kernel.
 #include <cuda.h>
+#include <cstdlib>
 #include <stdexcept>
 #include "../include/ddpt_nn.h"
 #include "../include/ddpt_common.cuh"
@@ -50,13 +51,20 @@ struct HaloArgs {
   int relu, out_fp32;
 };
 
-template <int BN, bool B_MN, bool B_RES>
-__global__ void __launch_bounds__(kThreads, 1)
+// NI = 2 (resident weights, BN <= 128): TWO MMA-issuing warps.  A 128 x 64 x 16 MMA is 32 tensor cycles, less than one
+// in-order thread needs to build and issue it (profiles/ncu_gemm_v2.txt: conv.3 data gradient, tensor pipe 39 % active,
+// the issuing lane 65 % busy with descriptor arithmetic + UTCHMMA).  Issuer j takes every second activation brick
+// (the 3 filter-row taps x 4 K-steps of one halo tile) and accumulates into its OWN TMEM accumulator; the epilogue adds
+// the two.  Both issuers run on different SM sub-partitions, so descriptor math proceeds in parallel while the tensor
+// pipe executes their MMAs in arrival order.
+template <int BN, bool B_MN, bool B_RES, int NI>
+__global__ void __launch_bounds__(kThreads + 32 * (NI - 1), 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const HaloArgs args, const int num_m_tiles, const int num_n_tiles) {
   constexpr int kBStageBytes = BN * kBlockK * 2;
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kTmemCols = 2 * BN * NI;
+  static_assert(NI == 1 || (NI == 2 && B_RES && BN <= 128), "two issuers: resident weights, 2 x 2 x BN TMEM columns");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_taps = args.taps_h * args.taps_w;
@@ -82,7 +90,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < args.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < args.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpilogueWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], NI); mbar_init(&tmem_empty[s], kEpilogueWarps); }
     mbar_init(b_ready, 1);
     fence_barrier_init();
   }
@@ -146,22 +154,25 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: every tap is a shifted view of the halo brick =====
+  } else if (warp == 1 || warp == 2 + kEpilogueWarps) {
+    // ===== MMA issuer(s): every tap is a shifted view of the halo brick =====
+    const int me = warp == 1 ? 0 : 1;                       // issuer index (NI == 2: warp 10 is the second issuer)
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       int a_s = 0, b_s = 0;
-      uint32_t a_phase = 0, b_phase = 0, t = 0;
+      uint32_t a_phase = 0, b_phase = 0, t = 0, brick = 0;
       if (B_RES) mbar_wait(b_ready, 0, 45);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 44);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + (acc * NI + me) * BN;
+        uint32_t started = 0;                               // this issuer's accumulator holds data of this tile
         for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
-          for (int cs = 0; cs < args.taps_w; ++cs) {
+          for (int cs = 0; cs < args.taps_w; ++cs, ++brick) {
             const int sa = a_s;
             const uint32_t a_ph = a_phase;
             if (++a_s == args.a_stages) { a_s = 0; a_phase ^= 1; }
+            if (NI > 1 && (brick & 1u) != (uint32_t)me) continue;      // the other issuer's brick
             mbar_wait(&a_full[sa], a_ph, 43);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_a + sa * args.a_slot_bytes);
@@ -188,9 +199,10 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               for (int k = 0; k < kBlockK / kUmmaK; ++k)
                 mma_bf16_ss(tmem_d, desc_advance(adesc0, k * (kUmmaK * 2)),
                             desc_advance(bdesc0, k * (B_MN ? kUmmaK * 128 : kUmmaK * 2)), kIdesc,
-                            (chunk | cs | dr | k) != 0 ? 1u : 0u);
+                            (started | dr | k) != 0 ? 1u : 0u);
               if (!B_RES) mma_commit(&b_empty[sb]);
             }
+            started = 1;
             mma_commit(&a_empty[sa]);
           }
         }
@@ -224,11 +236,17 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       for (int cc = 0; cc < kChunksPerWarp; ++cc) {
         const int c = half * kChunksPerWarp + cc;
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+        tmem_ld_32x32(tmem_base + (acc * NI) * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (NI > 1) {                                          // second issuer's partial sums
+          tmem_ld_32x32(tmem_base + (acc * NI + 1) * BN + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
         const int col = tile_n * BN + c * 32;
         if (args.bias != nullptr) {
 #pragma unroll
@@ -382,12 +400,29 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   int grid = total_tiles < sm_count() ? total_tiles : sm_count();
   grid -= grid % tiles_n_cols;
   if (grid < tiles_n_cols) grid = tiles_n_cols;
-  auto run = [&](auto kernel) {
+  auto run = [&](auto kernel, int threads) {
     DDPT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
+    launch_pdl(kernel, dim3(grid), dim3(threads), smem_bytes, stream, tmap_a, tmap_b, a, tiles_m, tiles_n_cols);
   };
-  if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true>);
-  else run(conv_gemm_halo_kernel<BN, B_MN, false>);
+  // Two issuing warps (DDPT_HALO_ISSUERS=2, opt-in): resident weights, at least two activation bricks per tile.  Measured
+  // on conv.3's data gradient (64 columns): 192 us with two issuers on an even 4-stage ring vs 167 us with one issuer on
+  // a 5-stage ring -- the in-order tensor pipe gains nothing from a second instruction stream once the first one's
+  // descriptor math is a single add (desc_advance), and the ring loses a stage.  Kept for experiments.
+  static const bool dual_ok = std::getenv("DDPT_HALO_ISSUERS") != nullptr && std::atoi(std::getenv("DDPT_HALO_ISSUERS")) == 2;
+  if constexpr (BN <= 128) {
+    if (resident && dual_ok && a.k_chunks * p.taps_w >= 2 && a.a_stages >= 2) {
+      // an EVEN ring: stage s then always belongs to issuer s % 2, which therefore observes every phase of that stage's
+      // barriers.  With an odd ring an issuer would see only every second phase of a stage, and a parity wait cannot tell
+      // "my brick has landed" from "the brick two laps ago had" when it runs ahead of the other issuer (seen as a sporadic
+      // launch failure in the first version).
+      a.a_stages &= ~1;
+      run(conv_gemm_halo_kernel<BN, B_MN, true, 2>, kThreads + 32);
+      DDPT_CUDA_CHECK(cudaGetLastError());
+      return p.stat_partials != nullptr ? grid : tiles_m;
+    }
+  }
+  if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true, 1>, kThreads);
+  else run(conv_gemm_halo_kernel<BN, B_MN, false, 1>, kThreads);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return p.stat_partials != nullptr ? grid : tiles_m;
 }

@@ -21,6 +21,9 @@
 #include "../include/umma.cuh"
 #include "tensor_map.h"
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -56,12 +59,24 @@ struct KernelArgs {
   int kbs;                      // K blocks (tap x 64-channel chunk) per pipeline stage: amortises the barrier round trip
   int a_w, a_h;                 // extent of the activation tensor (taps whose whole brick is out of range are skipped)
   int pair_interleave;          // CTA pair: the two row tiles of a unit are the same pixel brick of adjacent image groups
+  const int* schedule;          // optional host-planned work lists: schedule[cta * sched_len + k] = k-th unit of CTA (pair)
+  int sched_len;                // `cta`, -1 terminated; null: round robin (unit = cta + k * #ctas)
 };
+
+// k-th work unit of this CTA (pair), or -1 when it has none left.  Data-gradient tiles cost between 1 and taps_h x taps_w
+// filter taps once out-of-range taps are skipped, so a round-robin walk leaves some CTAs with 20-30 % more work than
+// the average; the launcher plans the lists with a longest-processing-time-first heuristic instead.
+__device__ __forceinline__ int work_unit(const KernelArgs& a, int cta, int num_ctas, int num_units, int k) {
+  if (a.schedule != nullptr) return k < a.sched_len ? __ldg(a.schedule + cta * a.sched_len + k) : -1;
+  const int unit = cta + k * num_ctas;
+  return unit < num_units ? unit : -1;
+}
+
 
 // Row tile -> brick coordinates.  Default order: brick column fastest, then brick row, then image group.  With
 // pair_interleave the two tiles of a CTA pair (tile_m = 2q, 2q+1) share the pixel position and take adjacent image
 // groups, so both need exactly the same filter taps (data gradient: border positions skip out-of-range taps).
-__device__ __forceinline__ void decode_tile(const KernelArgs& a, int tile_m, int& tw, int& th, int& tn) {
+__host__ __device__ __forceinline__ void decode_tile(const KernelArgs& a, int tile_m, int& tw, int& th, int& tn) {
   const int positions = a.tiles_w * a.tiles_h;
   int pos;
   if (a.pair_interleave) {
@@ -80,11 +95,11 @@ __device__ __forceinline__ void decode_tile(const KernelArgs& a, int tile_m, int
 // ('valid') convolution every tap qualifies; for the data gradient a brick at the border of the input image only
 // sees part of the filter -- with one-pixel bricks (128 images x 1 x 1) the MMA count drops from taps x pixels to the
 // nominal sum over pixels of the taps that actually reach them (Toy_Net conv.10: 576 instead of 900 per image group).
-__device__ __forceinline__ void tap_range(int origin, int box, int extent, int taps, int sign, int& lo, int& hi) {
+__host__ __device__ __forceinline__ void tap_range(int origin, int box, int extent, int taps, int sign, int& lo, int& hi) {
   lo = taps; hi = -1;
   for (int t = 0; t < taps; ++t) {
     const int start = origin + sign * t;
-    if (start + box > 0 && start < extent) { lo = min(lo, t); hi = max(hi, t); }
+    if (start + box > 0 && start < extent) { lo = lo < t ? lo : t; hi = hi > t ? hi : t; }
   }
   if (hi < 0) { lo = 0; hi = 0; }            // nothing in range (padding tile): one tap of zeros defines the accumulator
 }
@@ -92,16 +107,16 @@ __device__ __forceinline__ void tap_range(int origin, int box, int extent, int t
 struct TileTaps { int tx0, tx1, ty0, ty1; };
 // Union over the MC row tiles of a work unit (the leader issues one MMA stream for both CTAs).
 template <int MC>
-__device__ __forceinline__ TileTaps unit_taps(const KernelArgs& a, int tile_m0) {
+__host__ __device__ __forceinline__ TileTaps unit_taps(const KernelArgs& a, int tile_m0) {
   TileTaps r{a.taps_w, -1, a.num_taps / a.taps_w, -1};
 #pragma unroll
   for (int i = 0; i < MC; ++i) {
     int tw, th, tn, lo, hi;
     decode_tile(a, tile_m0 + i, tw, th, tn);
     tap_range(tw * a.box_w + a.a_w_off, a.box_w, a.a_w, a.taps_w, a.tap_sign, lo, hi);
-    r.tx0 = min(r.tx0, lo); r.tx1 = max(r.tx1, hi);
+    r.tx0 = r.tx0 < lo ? r.tx0 : lo; r.tx1 = r.tx1 > hi ? r.tx1 : hi;
     tap_range(th * a.box_h + a.a_h_off, a.box_h, a.a_h, a.num_taps / a.taps_w, a.tap_sign, lo, hi);
-    r.ty0 = min(r.ty0, lo); r.ty1 = max(r.ty1, hi);
+    r.ty0 = r.ty0 < lo ? r.ty0 : lo; r.ty1 = r.ty1 > hi ? r.ty1 : hi;
   }
   return r;
 }
@@ -128,7 +143,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM * MC, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
 
-  static_assert(MC == 1 || (MC == 2 && !B_RES && BN >= 128), "CTA pair: streamed weights, >= 64 columns per CTA");
+  // CTA pair: streamed weights; an MN-major weight tile is loaded in 64-column boxes, so a pair needs BN >= 128 there.
+  // K-major weights split at any BN: at BN = 64 each CTA stages 32 weight rows and one paired MMA (256 x 64 x 16) does
+  // the work of two single-CTA instructions -- the 64-column data gradient (Toy_Net conv.3) was ISSUE-bound at one
+  // 32-cycle MMA per instruction (tensor pipe 39 % active, profiles/ncu_gemm_v2.txt).
+  static_assert(MC == 1 || (MC == 2 && !B_RES && (BN >= 128 || !B_MN)), "CTA pair: streamed weights; MN-major needs BN >= 128");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // work units: (group of MC consecutive row tiles) x column block; CTA `rank` of a cluster takes row tile
@@ -197,7 +216,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       }
       int ring_s = 0;
       uint32_t ring_phase = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+      for (int wk = 0;; ++wk) {
+        const int unit = work_unit(args, unit0, unit_stride, num_units, wk);
+        if (unit < 0) break;
         const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
         int tw, th, tn;
         decode_tile(args, tile_m, tw, th, tn);
@@ -263,7 +284,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       int ring_s = 0;
       uint32_t ring_phase = 0, t = 0;
       if (B_RES) mbar_wait(b_ready, 0, 5);
-      for (int unit = unit0; unit < num_units; unit += unit_stride, ++t) {
+      for (int wk = 0;; ++wk, ++t) {
+        const int unit = work_unit(args, unit0, unit_stride, num_units, wk);
+        if (unit < 0) break;
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);       // epilogue has drained this accumulator
         tc_fence_after();
@@ -322,7 +345,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
     for (int cc = 0; cc < kChunksPerWarp; ++cc) acc_s1[cc] = acc_s2[cc] = 0.f;
     uint32_t t = 0;
-    for (int unit = unit0; unit < num_units; unit += unit_stride, ++t) {
+    for (int wk = 0;; ++wk, ++t) {
+      const int unit = work_unit(args, unit0, unit_stride, num_units, wk);
+      if (unit < 0) break;
       const int tile_n = unit % num_n_tiles, tile_m = (unit / num_n_tiles) * MC + rank;
       int tw, th, tn;
       decode_tile(args, tile_m, tw, th, tn);
@@ -433,6 +458,54 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   }
 }
 
+// ---- host-planned work lists (data gradient) ---------------------------------------------------------------------
+// Cost of a unit = K blocks it actually runs (taps that reach the brick x channel chunks) with a floor for the
+// epilogue; longest-processing-time-first onto the least loaded CTA (pair) that owns the unit's column block.  Plans are
+// cached per problem shape in device memory (allocated outside CUDA-graph capture: the step engine's first, eager step).
+struct PlanKey {
+  int v[16];
+  bool operator<(const PlanKey& o) const { return std::lexicographical_compare(v, v + 16, o.v, o.v + 16); }
+};
+struct Plan { int* dev; int len; };
+
+template <int MC>
+const Plan* plan_schedule(const KernelArgs& a, int num_units, int num_n_tiles, int num_ctas, cudaStream_t stream) {
+  static std::map<PlanKey, Plan> cache;
+  static std::mutex mu;
+  PlanKey key{{a.tiles_w, a.tiles_h, a.box_w, a.box_h, a.box_n, a.out_w, a.out_h, a.out_n, a.taps_w, a.num_taps,
+               a.k_chunks, a.a_w, a.a_h, a.pair_interleave, num_n_tiles * 4 + MC, num_ctas}};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+  std::vector<std::pair<int, int>> units(num_units);          // (cost, unit)
+  for (int u = 0; u < num_units; ++u) {
+    const TileTaps t = unit_taps<MC>(a, (u / num_n_tiles) * MC);
+    const int kb = (t.tx1 - t.tx0 + 1) * (t.ty1 - t.ty0 + 1) * a.k_chunks;
+    units[u] = {std::max(kb, 8) + 2, u};
+  }
+  std::stable_sort(units.begin(), units.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+  std::vector<std::vector<int>> lists(num_ctas);
+  std::vector<long long> load(num_ctas, 0);
+  for (const auto& cu : units) {
+    const int col = cu.second % num_n_tiles;
+    int best = -1;
+    for (int c = col; c < num_ctas; c += num_n_tiles)            // CTAs that own this column block (grid % num_n_tiles == 0)
+      if (best < 0 || load[c] < load[best]) best = c;
+    lists[best].push_back(cu.second);
+    load[best] += cu.first;
+  }
+  size_t len = 1;
+  for (const auto& l : lists) len = std::max(len, l.size() + 1);
+  std::vector<int> table(num_ctas * len, -1);
+  for (int c = 0; c < num_ctas; ++c) std::copy(lists[c].begin(), lists[c].end(), table.begin() + c * len);
+  Plan plan{nullptr, (int)len};
+  if (cudaMalloc(&plan.dev, table.size() * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  DDPT_CUDA_CHECK(cudaMemcpy(plan.dev, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return &cache.emplace(key, plan).first->second;
+}
+
 template <int BN, bool B_MN, bool B_RES, int MC = 1>
 int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   constexpr int kBStageBytes = (BN / MC) * kBlockK * 2;
@@ -535,6 +608,11 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   if (units < tiles_n_cols) units = tiles_n_cols;
   const int grid = units * MC;
   cfg.gridDim = dim3(grid);
+  if (p.tap_sign < 0 && a.num_taps > 1 && total_units > units && std::getenv("DDPT_NO_TILE_PLAN") == nullptr) {
+    // uneven tiles (border bricks skip filter taps) and more than one unit per CTA: hand every CTA a planned list
+    const Plan* plan = plan_schedule<MC>(a, total_units, tiles_n_cols, units, stream);
+    if (plan != nullptr) { a.schedule = plan->dev; a.sched_len = plan->len; }
+  }
   DDPT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_b, a, tiles_m, tiles_n_cols));
   return p.stat_partials != nullptr ? grid : tiles_m;   // statistic row groups (x4 rows) written
 }
@@ -545,6 +623,7 @@ int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStrea
   // resident weights: one column block, and taps*C*BLOCK_N*2 bytes + a 4-deep activation ring fit in shared memory
   const long long b_bytes = (long long)p.taps_h * p.taps_w * p.a_c * block_n * 2;
   const bool resident = p.n_total == block_n && b_bytes + 4 * kAStageBytes + 2048 <= 227 * 1024 && b_bytes < (1 << 20);
+  if (cta_pair && block_n == 64 && !p.b_mn_major) return launch_persistent_impl<64, false, false, 2>(p, stream);
   if (cta_pair && !resident && block_n >= 128) {          // CTA pairs (cta_group::2): 256-row tiles, weights split
     if (p.b_mn_major) {
       if (block_n == 128) return launch_persistent_impl<128, true, false, 2>(p, stream);

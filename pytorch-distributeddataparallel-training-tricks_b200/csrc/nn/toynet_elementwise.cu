@@ -1091,7 +1091,28 @@ head_kernel(HeadArgs a) {
   }
 }
 
+// w [c_out][taps][c_in] (the K-major forward weight) -> wt [c_in][taps][c_out]: the K-major operand of the data
+// gradient (reduction over c_out), which lets the 64-column data gradient run as a CTA pair.  144 KiB for conv.3.
+__global__ void __launch_bounds__(kThreads)
+transpose_taps_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int c_out, int taps, int c_in) {
+  pdl_wait();
+  pdl_trigger();
+  const int total = c_out * taps * c_in;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    const int co = i % c_out, t = (i / c_out) % taps, ci = i / (c_out * taps);       // i indexes wt
+    wt[i] = w[((size_t)co * taps + t) * c_in + ci];
+  }
+}
+
 }  // namespace
+
+void launch_transpose_taps(const __nv_bfloat16* w, __nv_bfloat16* wt, int c_out, int taps, int c_in, cudaStream_t s) {
+  const int total = c_out * taps * c_in;
+  int grid = (total + kThreads - 1) / kThreads;
+  if (grid > 4 * sm_count()) grid = 4 * sm_count();
+  launch_pdl(transpose_taps_kernel, dim3(grid), dim3(kThreads), 0, s, w, wt, c_out, taps, c_in);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+}
 
 // ---- launchers -------------------------------------------------------------------------------------
 int conv0_partial_rows() { return sm_count() * 2; }

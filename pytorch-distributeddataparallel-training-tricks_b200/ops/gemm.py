@@ -72,6 +72,15 @@ def pick_box_dgrad(out_n: int, out_h: int, out_w: int, kh: int, kw: int) -> Tupl
     return best
 
 
+def transpose_taps(w_km: torch.Tensor, taps: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[C_out, taps*C_in] -> [C_in, taps*C_out] (bf16): the data gradient's K-major weight operand."""
+    c_out, c_in = w_km.shape[0], w_km.shape[1] // taps
+    if out is None:
+        out = torch.empty((c_in, taps * c_out), dtype=torch.bfloat16, device=w_km.device)
+    require_native().transpose_taps(w_km, out, taps)
+    return out
+
+
 def use_persistent(flag: Optional[bool] = None) -> bool:
     """Persistent (one CTA per SM, double-buffered TMEM) GEMM kernels; DDPT_GEMM_PERSISTENT=0 disables."""
     if flag is not None:
@@ -175,8 +184,11 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
                block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None,
-               pair: Optional[bool] = None):
-    """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in]."""
+               pair: Optional[bool] = None, w_t: Optional[torch.Tensor] = None):
+    """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in].
+
+    ``w_t`` (optional, :func:`transpose_taps` of ``w_km``): K-major weights [C_in, taps*C_out]; with 64 input channels
+    they let the data gradient run on CTA pairs (DDPT_DGRAD64_PAIR=1)."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
     h, w = ho + kh - 1, wo + kw - 1
@@ -185,9 +197,16 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
         out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
     bn = _block_n(c_in, block_n)
     mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, pair)
+    b, b_mn = w_km, True
+    if (w_t is not None and bn == 64 and halo is not True and use_persistent(persistent) and use_cta_pair(pair)
+            and os.environ.get("DDPT_DGRAD64_PAIR", "0") == "1"):
+        # 64 input channels: the transposed weights are a K-major operand, which the CTA-pair kernel can split 32 + 32
+        # rows (one 256 x 64 MMA per instruction).  Measured 159 us vs 159 us for the two-issuer halo kernel on conv.3
+        # (every input pixel crosses L2 -> SM nine times here, 3.75 times there): opt-in.
+        mode, b, b_mn = 3, w_t, False
     if mode in (1, 3) and kh * kw > 1 and os.environ.get("DDPT_DGRAD_SKIP_TAPS", "1") != "0":
         box = pick_box_dgrad(n, h, w, kh, kw)       # the persistent kernels skip filter taps that miss the brick
-    ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], True,
+    ext.conv_gemm(dy, b, out.view(n * h * w, c_in), [n, h, w], list(box), [kh, kw], -1, [0, 0], b_mn,
                   None, False, None, 1, bn, mode)
     return out
 

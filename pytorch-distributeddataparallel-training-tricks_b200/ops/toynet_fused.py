@@ -65,6 +65,7 @@ class _Workspace:
         # fused BatchNorm statistics: fp64 accumulators [10][2][512] (rows 0-4 forward sum / sum of squares per layer,
         # rows 5-9 backward sum dz / sum dz*y), cleared once per training step
         self.stat = torch.zeros(10, 2 * 512, dtype=torch.float64, device=device)
+        self.wt3 = e(64, 9 * 128)                          # conv.3 weights as the data gradient's K-major operand
         # block-scaled fp8 copies of the activations feeding conv.7, conv.10 and dense.1 ("O1-fp8")
         self.q = {}
 
@@ -108,6 +109,7 @@ class FusedToyNet:
         # (reference: utils/customized.py:12-13 sets cudnn.deterministic).
         self.deterministic = deterministic()
         self._det_ws: Optional[torch.Tensor] = None
+        self.dgrad64_pair = os.environ.get("DDPT_DGRAD64_PAIR", "0") == "1"
         self.fused_stats = (compute != "fp8" and not deterministic()
                             and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
 
@@ -310,7 +312,10 @@ class FusedToyNet:
             off_critical_path(lambda k=k, pidx=pidx: gemm.conv_wgrad(ws.dy[k], ws.a[k - 1], 3, 3, out=grads[pidx],
                                                                      out_is_zero=True))
             ready(pidx)
-            g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1])
+            w_t = None
+            if c_in == 64 and self.dgrad64_pair:     # conv.3 on CTA pairs needs the K-major (tap-transposed) weights
+                w_t = gemm.transpose_taps(self._weight_bf16(pidx), 9, ws.wt3)
+            g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1], w_t=w_t)
         self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
         ready(3); ready(2)
         ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1], self.det_partials())

@@ -1,5 +1,6 @@
 """sm_100a kernel numerics vs plain PyTorch fp32 references (run on a B200: pytest -m gpu)."""
 import math
+import os
 
 import pytest
 import torch
@@ -128,6 +129,27 @@ def test_conv3x3_dgrad_skips_out_of_range_taps(ext, gemm_flavour, n, h, w, ci, c
     dx = gemm.conv_dgrad(dy, wk, 3, 3)
     assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
     # per-pixel check: a skipped tap that was needed would zero out whole border rows/columns
+    err = (dx.permute(0, 3, 1, 2).float() - want).abs().amax(dim=(0, 1))
+    assert float(err.max()) < 0.05 * float(want.abs().max()), err
+
+
+@pytest.mark.parametrize("n,h,w,co", [(8, 26, 26, 128), (130, 9, 11, 128), (256, 10, 10, 256), (5, 7, 9, 64)])
+def test_conv3x3_dgrad_64_channels_as_cta_pair(ext, gemm_flavour, n, h, w, co):
+    """C_in = 64: with the tap-transposed (K-major) weights the data gradient runs on cta_group::2 MMAs (256 x 64 x 16),
+    each CTA staging 32 weight rows; same numbers as the MN-major single-CTA path."""
+    from ddpt_b200.ops import gemm
+    ci = 64
+    dy, wk = _bf16(n, h - 2, w - 2, co, seed=41), _bf16(co, 9 * ci, scale=(9 * co) ** -0.5, seed=42)
+    w_t = gemm.transpose_taps(wk, 9)
+    assert torch.equal(w_t.view(ci, 9, co), wk.view(co, 9, ci).permute(2, 1, 0))
+    wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    want = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt)
+    os.environ["DDPT_DGRAD64_PAIR"] = "1"
+    try:
+        dx = gemm.conv_dgrad(dy, wk, 3, 3, w_t=w_t)
+    finally:
+        os.environ.pop("DDPT_DGRAD64_PAIR", None)
+    assert _rel_err(dx.permute(0, 3, 1, 2), want) < 1e-2
     err = (dx.permute(0, 3, 1, 2).float() - want).abs().amax(dim=(0, 1))
     assert float(err.max()) < 0.05 * float(want.abs().max()), err
 
