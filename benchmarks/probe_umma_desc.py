@@ -7,9 +7,9 @@ once with its halo can serve all filter taps as shifted descriptor views (see DE
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ddpt_b200.ops import require_native
+from probes.build import load as _load_probes
 
-ext = require_native()
+ext = _load_probes()
 torch.manual_seed(0)
 dev = "cuda"
 res = []

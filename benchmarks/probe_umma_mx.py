@@ -6,8 +6,8 @@ scale words are written to TMEM lane-by-lane with tcgen05.st, and the pattern of
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ddpt_b200.ops import require_native
-ext = require_native()
+from probes.build import load as _load_probes
+ext = _load_probes()
 dev = "cuda"
 ONE = 0x38
 A = torch.full((128, 128), ONE, dtype=torch.uint8, device=dev)

@@ -4,9 +4,9 @@
 // Tooling for benchmarks/probe_umma_mx.py; not on a hot path.
 #include <cuda.h>
 #include <stdexcept>
-#include "../include/ddpt_common.cuh"
-#include "../include/umma.cuh"
-#include "tensor_map.h"
+#include "ddpt_common.cuh"
+#include "umma.cuh"
+#include "nn/tensor_map.h"
 
 namespace ddpt {
 

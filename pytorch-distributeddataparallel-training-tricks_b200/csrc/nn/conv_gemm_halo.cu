@@ -57,7 +57,13 @@ struct HaloArgs {
 // (the 3 filter-row taps x 4 K-steps of one halo tile) and accumulates into its OWN TMEM accumulator; the epilogue adds
 // the two.  Both issuers run on different SM sub-partitions, so descriptor math proceeds in parallel while the tensor
 // pipe executes their MMAs in arrival order.
-template <int BN, bool B_MN, bool B_RES, int NI>
+//
+// KC > 0 (resident weights, 3x3 filter, KC channel chunks): the issuer's loops over (chunk, filter column, filter row,
+// K step) are fully unrolled with compile-time trip counts.  Every weight-tile descriptor is then `base + immediate`
+// and an activation view `brick base + dr * stride + k * 32 B`: two integer adds per MMA instead of the ~15-20
+// instructions of runtime tap arithmetic and descriptor encoding the generic loop spends -- on 64-column tiles (32
+// tensor cycles per MMA) that arithmetic, not the tensor pipe, set the pace (tensor pipe 39 % active).
+template <int BN, bool B_MN, bool B_RES, int NI, int KC>
 __global__ void __launch_bounds__(kThreads + 32 * (NI - 1), 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const HaloArgs args, const int num_m_tiles, const int num_n_tiles) {
@@ -65,6 +71,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
   constexpr uint32_t kTmemCols = 2 * BN * NI;
   static_assert(NI == 1 || (NI == 2 && B_RES && BN <= 128), "two issuers: resident weights, 2 x 2 x BN TMEM columns");
+  static_assert(KC == 0 || (B_RES && NI == 1), "unrolled issuer: resident weights, single issuer");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_taps = args.taps_h * args.taps_w;
@@ -166,6 +173,41 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 44);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (acc * NI + me) * BN;
+        if constexpr (KC > 0) {
+          // fixed 3x3 x KC shape: everything but the ring slot is a compile-time constant
+          constexpr int kSign = B_MN ? -1 : 1;              // data gradient (MN-major weights) walks the taps backwards
+          const uint64_t bdesc_base = B_MN ? make_smem_desc(smem_u32(smem_b), kBlockK * 128, 1024)
+                                           : make_smem_desc(smem_u32(smem_b), 0, 1024);
+          const uint32_t dr_stride = static_cast<uint32_t>(args.box_n) * 1024u;
+#pragma unroll
+          for (int chunk = 0; chunk < KC; ++chunk) {
+#pragma unroll
+            for (int cs = 0; cs < 3; ++cs, ++brick) {
+              const int sa = a_s;
+              const uint32_t a_ph = a_phase;
+              if (++a_s == args.a_stages) { a_s = 0; a_phase ^= 1; }
+              mbar_wait(&a_full[sa], a_ph, 43);
+              tc_fence_after();
+              const uint64_t adesc_base = make_smem_desc(smem_u32(smem_a + sa * args.a_slot_bytes), 0, 1024);
+#pragma unroll
+              for (int dr = 0; dr < 3; ++dr) {
+                constexpr int kDummy = 0; (void)kDummy;
+                const int r = kSign > 0 ? dr : 2 - dr;
+                const int sx = kSign > 0 ? cs : 2 - cs;
+                const uint32_t b_off = static_cast<uint32_t>(((r * 3 + sx) * KC + chunk) * kBStageBytes);
+                const uint64_t adesc_dr = desc_advance(adesc_base, dr * dr_stride);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  mma_bf16_ss(tmem_d, desc_advance(adesc_dr, k * (kUmmaK * 2)),
+                              desc_advance(bdesc_base, b_off + k * (B_MN ? kUmmaK * 128 : kUmmaK * 2)), kIdesc,
+                              (chunk | cs | dr | k) != 0 ? 1u : 0u);
+              }
+              mma_commit(&a_empty[sa]);
+            }
+          }
+          mma_commit(&tmem_full[acc]);
+          continue;
+        }
         uint32_t started = 0;                               // this issuer's accumulator holds data of this tile
         for (int chunk = 0; chunk < args.k_chunks; ++chunk) {
           for (int cs = 0; cs < args.taps_w; ++cs, ++brick) {
@@ -416,13 +458,21 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
       // "my brick has landed" from "the brick two laps ago had" when it runs ahead of the other issuer (seen as a sporadic
       // launch failure in the first version).
       a.a_stages &= ~1;
-      run(conv_gemm_halo_kernel<BN, B_MN, true, 2>, kThreads + 32);
+      run(conv_gemm_halo_kernel<BN, B_MN, true, 2, 0>, kThreads + 32);
       DDPT_CUDA_CHECK(cudaGetLastError());
       return p.stat_partials != nullptr ? grid : tiles_m;
     }
   }
-  if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true, 1>, kThreads);
-  else run(conv_gemm_halo_kernel<BN, B_MN, false, 1>, kThreads);
+  // fixed-shape issuer (3x3 filter, tap direction matching the operand layout, 1 or 2 channel chunks): DDPT_HALO_UNROLL=0
+  // keeps the generic loops
+  static const bool unroll_ok = std::getenv("DDPT_HALO_UNROLL") == nullptr || std::atoi(std::getenv("DDPT_HALO_UNROLL")) != 0;
+  const bool fixed = resident && unroll_ok && p.taps_h == 3 && p.taps_w == 3 && p.tap_sign == (B_MN ? -1 : 1);
+  if constexpr (BN <= 128) {
+    if (fixed && a.k_chunks == 1) { run(conv_gemm_halo_kernel<BN, B_MN, true, 1, 1>, kThreads); DDPT_CUDA_CHECK(cudaGetLastError()); return p.stat_partials != nullptr ? grid : tiles_m; }
+    if (fixed && a.k_chunks == 2) { run(conv_gemm_halo_kernel<BN, B_MN, true, 1, 2>, kThreads); DDPT_CUDA_CHECK(cudaGetLastError()); return p.stat_partials != nullptr ? grid : tiles_m; }
+  }
+  if (resident) run(conv_gemm_halo_kernel<BN, B_MN, true, 1, 0>, kThreads);
+  else run(conv_gemm_halo_kernel<BN, B_MN, false, 1, 0>, kThreads);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return p.stat_partials != nullptr ? grid : tiles_m;
 }
