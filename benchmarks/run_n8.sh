@@ -16,6 +16,7 @@ run bench_n4 150 $TR 4 --master-addr 127.0.0.1 --master-port 29603 bench.py --gp
 run bench_n2 150 $TR 2 --master-addr 127.0.0.1 --master-port 29604 bench.py --gpus 2 --steps 200 --warmup 10
 run bench_ref_n8 200 $TR 8 --master-addr 127.0.0.1 --master-port 29605 bench.py --gpus 8 --impl reference --steps 40 --warmup 5
 run resnet_ours 150 $TR 8 --master-addr 127.0.0.1 --master-port 29621 benchmarks/bench_resnet50.py --impl ours
+run resnet_ours_cudnn 150 $TR 8 --master-addr 127.0.0.1 --master-port 29623 benchmarks/bench_resnet50.py --impl ours --no_tc
 run resnet_torch 150 $TR 8 --master-addr 127.0.0.1 --master-port 29622 benchmarks/bench_resnet50.py --impl torch
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
 echo done

@@ -41,7 +41,16 @@ class _PointwiseConvFn(torch.autograd.Function):
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
         dx = gemm.linear_dgrad(dy, w_bf16) if ctx.needs_input_grad[0] else None
-        dw = gemm.linear_wgrad(dy, x2d).view(ctx.w_shape) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            c_out, c_in = dy.shape[1], x2d.shape[1]
+            if c_out % 128 == 0:                      # the wgrad kernel tiles its M (= C_out) dimension by 128
+                dw = gemm.linear_wgrad(dy, x2d)
+            elif c_in % 128 == 0:                     # dW^T = x^T dy has M = C_in: same kernel, operands swapped
+                dw = gemm.linear_wgrad(x2d, dy).t().contiguous()
+            else:                                     # 64 -> 64 (ResNet-50 has one such layer): library GEMM
+                dw = (dy.t() @ x2d).float()
+            dw = dw.view(ctx.w_shape)
         db = dy.float().sum(0) if ctx.has_bias and ctx.needs_input_grad[3] else None
         return dx, dw, None, db
 
