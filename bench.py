@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--comm_wire", default="fp32", choices=("fp32", "bf16"))
     ap.add_argument("--opt_level", default="O1", choices=("O1", "O1-fp8"),
                     help="O1: bf16 (headline).  O1-fp8: conv.7/conv.10/dense.1 forward on block-scaled fp8 tensor cores")
+    ap.add_argument("--skip_e2e", action="store_true", help="experiments only: device-timed loop, no end-to-end loops")
     ap.add_argument("--census", default=None, help="write a per-step kernel census (CUPTI) of our arm to this JSON file")
     ap.add_argument("--local_rank", "--local-rank", type=int, default=None)
     return ap.parse_args()
@@ -245,7 +246,7 @@ def run_ours(args):
         return images, epoch, out
 
     results = {}
-    for mode in ("pinned", "device"):
+    for mode in (() if args.skip_e2e else ("pinned", "device")):
         loader = BatchLoader(train_set, B, sampler, device, mode=mode)
         loader.quiet = True
         loader.max_batches = None
@@ -266,6 +267,16 @@ def run_ours(args):
             dist.all_reduce(tot)
         results[mode] = {"ms": ms, "images": float(tot.item()), "epochs": ep_end - ep, "loss": loss, "acc": acc,
                          "h2d_per_step": (loader.h2d_bytes - h2d0) / K}
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * B * K / ms_dev * 1e3, "n_gpus": world, "steps": K,
+                              "ms_per_step": ms_dev / K, "e2e": None, "clocks": clocks, "experiment": True,
+                              "config": {"comm": getattr(model, "comm", "none"),
+                                         "comm_wire": getattr(getattr(model, "backend", None), "wire_name", None)}}))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
     ms_e2e = results["pinned"]["ms"]
     loss, acc = results["pinned"]["loss"], results["pinned"]["acc"]
     h2d = int(results["pinned"]["h2d_per_step"])

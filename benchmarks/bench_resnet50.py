@@ -47,10 +47,12 @@ def main():
             for m in model.modules():
                 if isinstance(m, conv_modules.TensorCoreConv1x1):
                     m.__class__ = nn.Conv2d
-        net = DDP(model, device_ids=[local], bucket_cap_mb=25.0, comm="fused" if world > 1 else "auto",
-                  comm_wire=a.comm_wire) if world > 1 else model
         from ddpt_b200.engine import GraphedTrainStep
-        graphed = GraphedTrainStep(net, loss_fn, opt, x, y, warmup=3, use_graph=not a.no_graph)
+        cap = torch.cuda.Stream()                 # DDP is built under the stream the step is captured on (see graphed.py)
+        with torch.cuda.stream(cap):
+            net = DDP(model, device_ids=[local], bucket_cap_mb=25.0, comm="fused", comm_wire=a.comm_wire) if world > 1 else model
+        torch.cuda.synchronize()
+        graphed = GraphedTrainStep(net, loss_fn, opt, x, y, warmup=3, use_graph=not a.no_graph, stream=cap)
 
         def step():
             graphed(x, y)

@@ -98,6 +98,13 @@ def main():
         for bn, sk in ((64, 1), (128, 1), (128, 4), (64, 2)):
             t = timeit(lambda: gemm.linear_fwd(x, w1, None, out_dtype=torch.float32, split_k=sk, block_n=bn), flush=flush)
             rows.append(dict(op="dense.1.fwd", block_n=bn, split_k=sk, ms=t, tflops=fl / t / 1e9))
+        part = torch.zeros(296 * 2 * 512, device="cuda")
+        bias1 = torch.zeros(512, device="cuda")
+        for bn, sk in ((256, 8), (256, 4), (128, 4), (128, 8), (256, 16)):
+            t = timeit(lambda: gemm.linear_fwd_splitk(x, w1, bias1, part, split_k=sk, block_n=bn), flush=flush)
+            rows.append(dict(op="dense.1.fwd.splitk_slabs+finish(bf16 out + BN stats)", block_n=bn, split_k=sk, ms=t, tflops=fl / t / 1e9))
+        t = timeit(lambda: gemm.conv_fwd(x.view(1, 1, B, 8192), w1, 1, 1, bias1, False, part.new_zeros(148 * 8 * 512), None, block_n=64), flush=flush)
+        rows.append(dict(op="dense.1.fwd.persistent64(bf16 out + BN stats)", ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: gemm.linear_dgrad(dy, w1), flush=flush)
         rows.append(dict(op="dense.1.dgrad", ms=t, tflops=fl / t / 1e9))
         t = timeit(lambda: gemm.linear_dgrad(dy, w1, pair=True), flush=flush)

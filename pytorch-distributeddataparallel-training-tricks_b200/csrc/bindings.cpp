@@ -127,7 +127,8 @@ void cast_bf16(at::Tensor src, at::Tensor dst) {
 int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_t> out_nhw,
                   std::vector<int64_t> box_nhw, std::vector<int64_t> taps_hw, int64_t tap_sign,
                   std::vector<int64_t> a_off_hw, bool b_mn_major, c10::optional<at::Tensor> bias, bool relu,
-                  c10::optional<at::Tensor> stat_partials, int64_t split_k, int64_t block_n, int64_t mode) {
+                  c10::optional<at::Tensor> stat_partials, int64_t split_k, int64_t block_n, int64_t mode,
+                  bool split_slabs) {
   check_cuda(a, "a", at::kBFloat16); check_cuda(b, "b", at::kBFloat16);
   TORCH_CHECK(a.dim() == 4 && a.is_contiguous(), "a must be contiguous [N,H,W,C]");
   TORCH_CHECK(b.dim() == 2 && b.stride(1) == 1, "b must be 2-D with unit inner stride");
@@ -166,6 +167,11 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
     }
   }
   p.split_k = (int)split_k;
+  if (split_slabs && split_k > 1) {       // out is [split_k * rows, ld]: one fp32 slab per split, plain stores
+    const int64_t rows = (int64_t)p.out_n * p.out_h * p.out_w;
+    TORCH_CHECK(p.out_fp32 && out.size(0) >= split_k * rows && mode == 0, "split slabs: fp32 [split_k * rows, N] output, per-tile kernel");
+    p.split_slab_stride = rows * p.ld_out;
+  }
   if (p.stat_partials != nullptr) {
     const int64_t tiles = (int64_t)((p.out_w + p.box_w - 1) / p.box_w) * ((p.out_h + p.box_h - 1) / p.box_h) *
                           ((p.out_n + p.box_n - 1) / p.box_n);
@@ -222,7 +228,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("cast_bf16", &cast_bf16);
   m.def("conv_gemm", &conv_gemm, py::arg("a"), py::arg("b"), py::arg("out"), py::arg("out_nhw"), py::arg("box_nhw"),
         py::arg("taps_hw"), py::arg("tap_sign"), py::arg("a_off_hw"), py::arg("b_mn_major"), py::arg("bias"),
-        py::arg("relu"), py::arg("stat_partials"), py::arg("split_k"), py::arg("block_n"), py::arg("mode"));
+        py::arg("relu"), py::arg("stat_partials"), py::arg("split_k"), py::arg("block_n"), py::arg("mode"),
+        py::arg("split_slabs") = false);
+  m.def("splitk_finish", [](at::Tensor slabs, int64_t splits, at::Tensor out, c10::optional<at::Tensor> stat_partials) {
+    TORCH_CHECK(slabs.is_cuda() && slabs.scalar_type() == at::kFloat && slabs.is_contiguous() && slabs.dim() == 2);
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.is_contiguous() && out.dim() == 2);
+    const int64_t rows = out.size(0), cols = out.size(1);
+    TORCH_CHECK(slabs.size(0) == splits * rows && slabs.size(1) == cols, "slabs must be [splits * rows, cols]");
+    float* part = nullptr;
+    if (stat_partials.has_value()) {
+      TORCH_CHECK(stat_partials->scalar_type() == at::kFloat && stat_partials->numel() >= (int64_t)ddpt::splitk_finish_max_rows() * 2 * cols);
+      part = stat_partials->data_ptr<float>();
+    }
+    c10::cuda::CUDAGuard guard(out.device());
+    return (int64_t)ddpt::launch_splitk_finish(slabs.data_ptr<float>(), (int)splits, rows * cols, (int)rows, (int)cols,
+                                               reinterpret_cast<__nv_bfloat16*>(out.data_ptr()), part, current_stream());
+  });
   m.def("wgrad_gemm", &wgrad_gemm);
   ddpt_bind_extra(m);
 }

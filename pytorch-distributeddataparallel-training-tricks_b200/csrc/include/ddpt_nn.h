@@ -42,6 +42,8 @@ struct ConvGemmProblem {
                                            // partial rows, and the consumer pass derives the BatchNorm coefficients itself
                                            // (no *_finalize launch).  Unordered adds: use stat_partials for bit-stable runs.
   int split_k;                             // K splits (fp32 output only)
+  long long split_slab_stride;             // > 0: split z stores its partial tile at out + z * stride (plain stores, no
+                                           // atomics); splitk_finish folds the slabs in order (+ bf16 pack + BN statistics)
 };
 
 // block_n in {64, 128, 256}; returns the number of M tiles launched.
@@ -52,6 +54,13 @@ int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStrea
 // Halo-reuse variant: the activation brick (+halo) is loaded once per channel chunk and every filter tap is a
 // shifted descriptor view; requires box_w == 8 and box_h * box_n <= 16.  Same return convention as persistent.
 int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
+
+// Fold `splits` fp32 slabs [rows, cols] (stride slab_stride elements) in split order into a bf16 matrix and, optionally,
+// BatchNorm column statistics as partial rows [blocks][2][cols] (returns the number of rows written) -- the second half
+// of a split-K linear layer whose output tile grid alone cannot fill the GPU (Toy_Net dense.1: 64 tiles on 148 SMs).
+int launch_splitk_finish(const float* slabs, int splits, long long slab_stride, int rows, int cols,
+                         __nv_bfloat16* out, float* stat_partials, cudaStream_t stream);
+int splitk_finish_max_rows();
 
 // Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,
 // reduction over the pixel bricks; fp32 accumulate into a zero-initialised or beta=1 output).

@@ -46,6 +46,7 @@ struct KernelArgs {
   float* stat_partials;
   double* stat_accum;
   int relu, out_fp32, a_rows_bytes;
+  long long slab_stride;        // split-K: > 0 = every split stores its own slab (no atomics)
 };
 
 template <int BN, bool B_MN>
@@ -213,7 +214,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (valid) {
         if (args.out_fp32) {
           float* o = static_cast<float*>(args.out) + out_row * args.ld_out + col;
-          if (gridDim.z > 1) {
+          if (args.slab_stride > 0) o += static_cast<long long>(blockIdx.z) * args.slab_stride;
+          if (gridDim.z > 1 && args.slab_stride == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(o + j, f[j]);
           } else {
@@ -263,6 +265,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
   a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
+  a.slab_stride = p.split_k > 1 ? p.split_slab_stride : 0;
 
   if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)
     throw std::runtime_error("conv_gemm: unsupported shape (C % 64, N % BLOCK_N, brick <= 128 rows)");
@@ -319,6 +322,66 @@ int launch_conv_gemm(const ConvGemmProblem& p, int block_n, cudaStream_t stream)
     }
   }
   throw std::runtime_error("conv_gemm: block_n must be 64, 128 or 256");
+}
+
+
+// ---- split-K second half ------------------------------------------------------------------------------------------
+namespace {
+constexpr int kFinishThreads = 256;
+
+__global__ void __launch_bounds__(kFinishThreads)
+splitk_finish_kernel(const float* __restrict__ slabs, int splits, long long slab_stride, int rows, int cols,
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ stat_partials) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float s_part[];                       // [rows_per_blk][2][cols] ordered block fold
+  const int cv = cols >> 3;
+  const int v = threadIdx.x % cv, lane_row = threadIdx.x / cv, rows_per_blk = kFinishThreads / cv;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (int r = blockIdx.x * rows_per_blk + lane_row; r < rows; r += gridDim.x * rows_per_blk) {
+    const float* src = slabs + (long long)r * cols + v * 8;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int z = 0; z < splits; ++z) {                    // fixed split order: deterministic
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src + z * slab_stride));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(src + z * slab_stride) + 1);
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + (long long)r * cols + v * 8) = pk;
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+  }
+  if (stat_partials == nullptr) return;
+  float* mine = s_part + (size_t)lane_row * 2 * cols;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mine[v * 8 + j] = s1[j]; mine[cols + v * 8 + j] = s2[j]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * cols; i += kFinishThreads) {
+    float tot = 0.f;
+    for (int r = 0; r < rows_per_blk; ++r) tot += s_part[(size_t)r * 2 * cols + i];
+    stat_partials[(size_t)blockIdx.x * 2 * cols + i] = tot;
+  }
+}
+}  // namespace
+
+int splitk_finish_max_rows() { return sm_count() * 2; }
+
+int launch_splitk_finish(const float* slabs, int splits, long long slab_stride, int rows, int cols,
+                         __nv_bfloat16* out, float* stat_partials, cudaStream_t stream) {
+  if (cols % 8 != 0 || kFinishThreads % (cols / 8) != 0) throw std::runtime_error("splitk_finish: cols must be 8 x a divisor of 256");
+  const int rows_per_blk = kFinishThreads / (cols / 8);
+  int grid = (rows + rows_per_blk - 1) / rows_per_blk;
+  if (grid > splitk_finish_max_rows()) grid = splitk_finish_max_rows();
+  const size_t smem = (size_t)rows_per_blk * 2 * cols * sizeof(float);
+  launch_pdl(splitk_finish_kernel, dim3(grid), dim3(kFinishThreads), smem, stream, slabs, splits, slab_stride, rows, cols, out,
+             stat_partials);
+  DDPT_CUDA_CHECK(cudaGetLastError());
+  return grid;
 }
 
 }  // namespace ddpt

@@ -13,6 +13,15 @@ replay contains forward, backward, bucketed communication and the optimizer with
 B200 a ResNet-50 step at 64 images per GPU is launch-bound in eager mode; the graph is what makes the per-GPU
 batch of BASELINE.json config 4 run at hardware speed.
 
+Stream rule (the same one torch documents for its own DDP under graph capture): autograd runs a parameter's
+AccumulateGrad node on the stream that was current when the node was created, and the DDP reducer keeps those nodes
+alive (its hooks hang off them).  Construct the DDP wrapper under the stream the step will be captured on::
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        net = DistributedDataParallel(model, device_ids=[rank], comm="fused")
+    step = GraphedTrainStep(net, loss_fn, optimizer, x, y, stream=s)
+
 Reference call sites replaced: the body of the batch loop in utils/process.py:17-28."""
 from __future__ import annotations
 
@@ -26,7 +35,7 @@ from .. import amp
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer, example_input: torch.Tensor,
                  example_target: torch.Tensor, warmup: int = 3, autocast_dtype: Optional[torch.dtype] = None,
-                 use_graph: bool = True):
+                 use_graph: bool = True, stream: Optional[torch.cuda.Stream] = None):
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.autocast_dtype = autocast_dtype
         self.static_x = example_input.clone()
@@ -39,7 +48,8 @@ class GraphedTrainStep:
         self._sgd = optimizer.optimizer if self._lookahead is not None else optimizer
         self._fused = getattr(self._sgd, "_fused", None)
         # eager warm-up on a side stream: allocator pools, cuDNN plans, momentum / slow-weight buffers, tile plans
-        side = torch.cuda.Stream(device=example_input.device)
+        side = stream if stream is not None else torch.cuda.Stream(device=example_input.device)
+        self.stream = side
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
@@ -50,7 +60,7 @@ class GraphedTrainStep:
             if self._fused is not None:
                 self._fused.prepare_for_capture(self._sgd, self._lookahead)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._body()
 
     def _body(self) -> None:

@@ -315,6 +315,26 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     return y.view(m, w.shape[0]), tiles
 
 
+def linear_fwd_splitk(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                      stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      split_k: int = 8, block_n: int = 256):
+    """y [M, N] bf16 = x [M, K] @ w [N, K]^T (+ bias) for layers whose tile grid is too small to fill the GPU (Toy_Net
+    dense.1: 1024 x 512 outputs = 64 tiles of 128 x 64 on 148 SMs, each streaming K = 8192 and bound by its own SM's L2
+    ingest).  ``split_k`` CTAs share a 128 x ``block_n`` tile's reduction and store fp32 slabs (no atomics); one
+    bandwidth-bound pass folds the slabs in order, packs bf16 and emits the BatchNorm column statistics as partial rows.
+    Returns ``(y, partial_rows)``."""
+    ext = require_native()
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    slabs = _slab(x.device, split_k * m * n)[: split_k * m * n].view(split_k * m, n)
+    ext.conv_gemm(x.view(1, 1, m, k), w, slabs, [1, 1, m], list(pick_box(1, 1, m)), [1, 1], 1, [0, 0], False, bias, False,
+                  None, split_k, block_n, 0, True)
+    rows = ext.splitk_finish(slabs, split_k, out, stat_partials)
+    return out, rows
+
+
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: Optional[int] = None,
                  persistent: Optional[bool] = None, pair: Optional[bool] = None):
     """dx [M, K] = dy [M, N] @ w [N, K]."""

@@ -110,6 +110,7 @@ class FusedToyNet:
         self.deterministic = deterministic()
         self._det_ws: Optional[torch.Tensor] = None
         self.dgrad64_pair = os.environ.get("DDPT_DGRAD64_PAIR", "0") == "1"
+        self.dense_splitk = int(os.environ.get("DDPT_DENSE_SPLITK", "8"))
         self.fused_stats = (compute != "fp8" and not deterministic()
                             and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
 
@@ -118,6 +119,8 @@ class FusedToyNet:
         fwd = 1 + 1 + 1 + 3 * 3 + 3              # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio (head: in bwd)
         bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
         bwd += 1 + 2                             # flatten -> channels-last transpose | split-K slab reductions (conv.3, conv.10 wgrad)
+        if self.dense_splitk > 1 and not self.fused_stats and batch >= 256 and self.compute != "fp8":
+            fwd += 1                             # dense.1: split-K GEMM + slab fold / statistics pass
         if self.fused_stats:
             fwd -= 5                             # no bn_finalize launches
             bwd -= 5                             # no bn_bwd_finalize launches
@@ -249,10 +252,17 @@ class FusedToyNet:
             xq, xs = ws.fp8_buffers(4, ws.a[3])
             wq, wsc = self._weight_fp8(16)
             _, tiles = gemm.linear_fwd_mxfp8(xq, xs, wq, wsc, P[17].detach(), False, part, y4)
+            rows4 = 4 * tiles
+        elif self.dense_splitk > 1 and not fused and batch >= 256:
+            # 8 x 8 output tiles cannot fill 148 SMs and each streams K = 8192 through one SM's L2 port: split the
+            # reduction over `dense_splitk` CTAs per 128 x 256 tile (fp32 slabs), fold + pack + statistics in one pass
+            _, rows4 = gemm.linear_fwd_splitk(ws.a[3], self._weight_bf16(16), P[17].detach(), part, y4,
+                                              split_k=self.dense_splitk, block_n=256)
         else:
             _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(),
                                      False, stat_out(4, 512), y4.view(1, 1, batch, 512), block_n=64)
-        self._bn_act(4, ws, train, fused, 4 * tiles, float(batch), False, False, (None, None))
+            rows4 = 4 * tiles
+        self._bn_act(4, ws, train, fused, rows4, float(batch), False, False, (None, None))
         if not head:       # training step engine: the backward head launch also produces loss / accuracy
             return ws.logits
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)

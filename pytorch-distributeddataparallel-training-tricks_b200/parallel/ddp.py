@@ -152,13 +152,18 @@ class DistributedDataParallel(nn.Module):
             return
         self._buffer_floats = cursor // 4
         region = backend.allocate_buffers(self._buffer_floats)
-        raw = region.view(torch.uint8)
+        storage = region.untyped_storage()
+        base = region.storage_offset() * region.element_size()
         views = {}
         with torch.no_grad():
             for mod, name, buf, off in slots:
                 if off not in views:
-                    nbytes = buf.numel() * buf.element_size()
-                    v = raw[off: off + nbytes].view(buf.dtype).view(buf.shape)
+                    # a FRESH tensor over the region's storage, not a view of `region`: views of one base share a version
+                    # counter, and autograd saves BatchNorm's running statistics for backward -- with shared counters
+                    # the in-place update of one layer's statistics would invalidate every other layer's saved tensors
+                    # ("modified by an inplace operation", seen on ResNet-50)
+                    v = torch.empty(0, dtype=buf.dtype, device=self.device)
+                    v.set_(storage, (base + off) // buf.element_size(), buf.shape, buf.contiguous().stride())
                     v.copy_(buf)
                     views[off] = v
                 mod._buffers[name] = views[off]

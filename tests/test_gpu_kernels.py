@@ -57,6 +57,23 @@ def test_linear_fwd_split_k(ext, gemm_flavour):
     assert _rel_err(y, x.float() @ w.float().t()) < 2e-3
 
 
+@pytest.mark.parametrize("m,n,k,split,bn", [(1024, 512, 8192, 8, 256), (608, 512, 8192, 4, 128), (256, 256, 1024, 2, 256)])
+def test_linear_fwd_splitk_slabs_and_statistics(ext, m, n, k, split, bn):
+    """Split-K linear: fp32 slabs (no atomics) folded in split order, bf16 output, BatchNorm partial rows."""
+    from ddpt_b200.ops import gemm
+    x, w = _bf16(m, k, seed=51), _bf16(n, k, scale=k ** -0.5, seed=52)
+    bias = torch.randn(n, device="cuda")
+    part = torch.zeros(ext.bn_bwd_partial_rows() * 2 * n, device="cuda")
+    y, rows = gemm.linear_fwd_splitk(x, w, bias, part, split_k=split, block_n=bn)
+    want = x.float() @ w.float().t() + bias
+    assert _rel_err(y, want) < 1e-2
+    stats = part[: rows * 2 * n].view(rows, 2, n).double().sum(0)
+    torch.testing.assert_close(stats[0], want.double().sum(0), rtol=2e-3, atol=0.05 * math.sqrt(m))
+    torch.testing.assert_close(stats[1], (want.double() ** 2).sum(0), rtol=5e-3, atol=1e-2)
+    y2, _ = gemm.linear_fwd_splitk(x, w, bias, None, split_k=split, block_n=bn)
+    assert torch.equal(y, y2)                                    # ordered fold: bit-reproducible
+
+
 @pytest.mark.parametrize("m,n,k", [(256, 128, 128), (1024, 8192, 512), (304, 512, 64)])
 def test_linear_dgrad_mn_major_b(ext, gemm_flavour, m, n, k):
     """dx[M,K] = dy[M,N] @ w[N,K] -- B operand consumed MN-major."""

@@ -261,8 +261,9 @@ def _buffers_broadcast_by_our_kernel(rank, world):
     from ddpt_b200.parallel import DistributedDataParallel as DDP
     dev = torch.device("cuda", rank)
     torch.manual_seed(rank)
-    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Flatten(), nn.Linear(8 * 6 * 6, 4)).to(dev)
-    bn = net[1]
+    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Conv2d(8, 8, 1), nn.BatchNorm2d(8), nn.ReLU(),
+                        nn.Flatten(), nn.Linear(8 * 6 * 6, 4)).to(dev)          # two BatchNorms: their re-homed buffers
+    bn = net[1]                                                                    # must not share a version counter
     bn.running_mean.fill_(float(rank + 1)); bn.running_var.fill_(float(10 * (rank + 1))); bn.num_batches_tracked.fill_(rank + 5)
     ddp = DDP(net, device_ids=[rank], comm="fused", bucket_cap_mb=0.001)
     # constructor: rank 0's parameters and buffers everywhere, through our broadcast kernel
@@ -284,6 +285,8 @@ def _buffers_broadcast_by_our_kernel(rank, world):
         assert torch.equal(got, ref), f"step {step}: rank {rank} running_mean differs from rank 0"
         assert int(bn.num_batches_tracked) == 5                # ... and are pulled back to rank 0's values
     assert ddp.backend.broadcasts - b0 == 3
+    ddp.train()                                                # train-mode backward through both BatchNorms (saved statistics)
+    ddp(torch.randn(4, 3, 8, 8, device=dev)).sum().backward()
     sd = ddp.state_dict()
     assert sd["module.1.num_batches_tracked"].dtype == torch.int64
     return ddp.backend.provider
@@ -302,7 +305,7 @@ def _odd_world_buckets(rank, world):
     torch.manual_seed(0)
     net = nn.Sequential(nn.Linear(37, 301), nn.ReLU(), nn.Linear(301, 10)).to(dev)
     for wire in ("fp32", "bf16"):
-        ddp = DDP(net, device_ids=[rank], comm="fused", bucket_cap_mb=0.02, comm_wire=wire, tail_bucket_kb=1)
+        ddp = DDP(net, device_ids=[rank], comm="fused", bucket_cap_mb=0.005, comm_wire=wire, tail_bucket_kb=1)
         assert all(b.numel % (8 * world) == 0 for b in ddp.buckets) and len(ddp.buckets) >= 2
         x = torch.randn(8, 37, device=dev) + rank
         ddp.zero_grad()
@@ -356,3 +359,60 @@ def _engine_deterministic_world(rank, world):
 def test_deterministic_mode_world2_is_bit_reproducible():
     _need_gpus(2)
     run_gpu_ranks(_engine_deterministic_world, 2)
+
+
+def _graphed_generic_ddp(rank, world):
+    """engine.GraphedTrainStep on a generic autograd model under our DDP: forward, backward with the reducer's fused
+    all-reduce launched from autograd hooks, loss scaling and the fused optimizer captured as ONE CUDA graph; ranks
+    stay bit-identical and the loss follows the eager trajectory."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from ddpt_b200 import amp
+    from ddpt_b200.engine import GraphedTrainStep
+    from ddpt_b200.ops.conv_modules import TensorCoreConv1x1
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    from ddpt_b200.utils import same_seeds
+    dev = torch.device("cuda", rank)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Sequential(nn.Conv2d(3, 64, 3, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU())
+            self.pw = TensorCoreConv1x1(64, 128, 1, bias=False)
+            self.bn = nn.BatchNorm2d(128)
+            self.head = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(128, 10))
+
+        def forward(self, x):
+            return self.head(F.relu(self.bn(self.pw(self.stem(x)))))
+
+    g = torch.Generator(device=dev).manual_seed(50 + rank)
+    xs = [torch.randn(16, 3, 16, 16, device=dev, generator=g).contiguous(memory_format=torch.channels_last) for _ in range(8)]
+    ys = [(x.mean((1, 2, 3)) > 0).long() + 2 * (x[:, 0, 0, 0] > 0).long() for x in xs]
+    loss_fn = nn.CrossEntropyLoss()
+    out = {}
+    for mode in ("graph", "eager"):
+        amp.reset()
+        same_seeds(9)
+        model = Net().to(dev).to(memory_format=torch.channels_last)
+        opt = Lookahead(SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True), k=3, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+        cap = torch.cuda.Stream()
+        with torch.cuda.stream(cap):
+            ddp = DDP(model, device_ids=[rank], comm="fused", bucket_cap_mb=0.05)
+        torch.cuda.synchronize()
+        step = GraphedTrainStep(ddp, loss_fn, opt, xs[0], ys[0], warmup=2, use_graph=(mode == "graph"), stream=cap)
+        losses = [float(step(x, y)) for x, y in zip(xs, ys)]
+        assert (step.replays == len(xs)) == (mode == "graph")
+        flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()])
+        ref = flat.clone(); dist.broadcast(ref, 0)
+        assert torch.equal(flat, ref), f"ranks diverged ({mode})"
+        out[mode] = losses
+    for a, b in zip(out["graph"], out["eager"]):
+        assert abs(a - b) <= 0.05 * abs(b) + 5e-3, (out["graph"], out["eager"])
+    return out["graph"][-1]
+
+
+def test_graphed_train_step_with_ddp_hooks_world2():
+    _need_gpus(2)
+    run_gpu_ranks(_graphed_generic_ddp, 2)
