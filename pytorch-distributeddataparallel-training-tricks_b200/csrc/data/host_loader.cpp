@@ -56,7 +56,12 @@ class PinnedGatherLoader {
       if (src[i] < 0 || src[i] >= num_rows_) throw std::out_of_range("sample index out of range");
     py::gil_scoped_release nogil;
     std::unique_lock<std::mutex> lk(mu_);
-    cv_.wait(lk, [this] { return active_workers_ == 0; });       // previous epoch fully drained
+    // a previous (possibly speculative, never consumed) epoch may still have workers parked on "slot free": tell
+    // them to drop it, then wait until every worker has left the batch loop
+    abort_ = true;
+    cv_.notify_all();
+    cv_.wait(lk, [this] { return active_workers_ == 0; });
+    abort_ = false;
     indices_.assign(src, src + n);
     num_batches_ = num_batches;
     for (auto& s : slots_) { s.batch = -1; s.ready = false; s.free = true; }
@@ -115,8 +120,9 @@ class PinnedGatherLoader {
         {
           std::unique_lock<std::mutex> lk(mu_);
           // a slot is reusable once the consumer released the batch that used it `slots` batches ago
-          cv_.wait(lk, [&] { return stop_ || (slots_[slot].free && next_consume_ + (int64_t)slots_.size() > b); });
+          cv_.wait(lk, [&] { return stop_ || abort_ || (slots_[slot].free && next_consume_ + (int64_t)slots_.size() > b); });
           if (stop_) return;
+          if (abort_) break;
           slots_[slot].free = false;
         }
         const int64_t begin = b * batch_, end = std::min(total, begin + batch_);
@@ -155,6 +161,7 @@ class PinnedGatherLoader {
   uint64_t generation_ = 0;
   int active_workers_ = 0;
   bool stop_ = false;
+  bool abort_ = false;       // start_epoch: abandon the epoch in progress
   std::atomic<int64_t> gathered_{0};
 };
 

@@ -52,6 +52,7 @@ class BatchLoader:
         self.h2d_bytes = 0
         self.samples_yielded = 0
         self.quiet = False          # True: iterate_loader shows no progress bar
+        self.prefetch_next_epoch = True   # pinned mode: start gathering epoch e+1 while epoch e's last step runs
 
     # -- sizing -----------------------------------------------------------
     def _num_samples(self) -> int:
@@ -77,7 +78,12 @@ class BatchLoader:
                 self.samples_yielded += int(sel.numel())
                 yield (img.float().div_(255.0) if self.as_float else img), self._dev_labels.index_select(0, sel)
         elif self.mode == "pinned":
-            for img, tgt, nbytes in self._native.epoch(idx, nb):
+            def next_epoch():
+                # speculation: the caller will ask for the following epoch with the same batch budget
+                if self.sampler is None or not self.prefetch_next_epoch:
+                    return None
+                return self.sampler.indices_for(self.sampler.epoch + 1), nb
+            for img, tgt, nbytes in self._native.epoch(idx, nb, next_epoch):
                 self.h2d_bytes += nbytes
                 self.samples_yielded += int(tgt.numel())
                 yield (img.float().div_(255.0) if self.as_float else img), tgt

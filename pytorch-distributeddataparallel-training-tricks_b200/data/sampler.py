@@ -32,6 +32,8 @@ class ShardedSampler:
         self.epoch = 0
         self._cache = {}            # epoch -> indices; filled one epoch ahead by a background thread
         self._prefetch = None
+        import threading
+        self._lock = threading.Lock()
         if drop_last and self.dataset_len % self.num_replicas:
             self.num_samples = math.ceil((self.dataset_len - self.num_replicas) / self.num_replicas)
         else:
@@ -45,22 +47,31 @@ class ShardedSampler:
         """This rank's sample indices for the current epoch (int64, CPU).  The next epoch's permutation is
         computed on a background thread while this epoch trains (``randperm`` releases the GIL), so the host
         never stalls the device at an epoch boundary."""
+        return self.indices_for(self.epoch)
+
+    def indices_for(self, epoch: int) -> torch.Tensor:
+        """Indices of ``epoch`` (cached); also starts computing ``epoch + 1`` in the background."""
         import threading
-        if self._prefetch is not None:
-            self._prefetch.join()
+        with self._lock:
+            pending = self._prefetch
+        if pending is not None:
+            pending.join()
+        with self._lock:
             self._prefetch = None
-        cur = self._cache.pop(self.epoch, None)
+            cur = self._cache.get(epoch)
         if cur is None:
-            cur = self._indices_for(self.epoch)
-        self._cache.clear()
-        nxt = self.epoch + 1
-
-        def work():
-            self._cache[nxt] = self._indices_for(nxt)
-
-        if self.shuffle:
-            self._prefetch = threading.Thread(target=work, daemon=True)
-            self._prefetch.start()
+            cur = self._indices_for(epoch)
+        with self._lock:
+            self._cache = {e: v for e, v in self._cache.items() if e >= epoch}     # drop the past
+            self._cache[epoch] = cur
+            nxt = epoch + 1
+            if self.shuffle and nxt not in self._cache:
+                def work():
+                    val = self._indices_for(nxt)
+                    with self._lock:
+                        self._cache[nxt] = val
+                self._prefetch = threading.Thread(target=work, daemon=True)
+                self._prefetch.start()
         return cur
 
     def _indices_for(self, epoch: int) -> torch.Tensor:

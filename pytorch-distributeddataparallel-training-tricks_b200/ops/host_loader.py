@@ -38,10 +38,20 @@ class PinnedGatherLoader:
                                               row, self.batch_size, [t.data_ptr() for t in self.img_slots],
                                               [t.data_ptr() for t in self.lbl_slots], threads)
         self.image_shape = tuple(images.shape[1:])
+        self._armed = None          # (indices, num_batches) of a speculatively started epoch
 
-    def epoch(self, indices: torch.Tensor, num_batches: int) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
+    def epoch(self, indices: torch.Tensor, num_batches: int, next_epoch=None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
+        """Yield the batches of one epoch.  ``next_epoch`` (optional callable -> (indices, num_batches) or None): as soon
+        as this epoch's last batch has been handed out, the workers start gathering the NEXT epoch's first batches into
+        the free slots, so the following ``epoch()`` call finds them ready (no cold start at the epoch boundary -- with 8
+        GPUs an MNIST epoch is 8 steps, ~12 ms of device time).  If the next call asks for something else, the
+        speculative work is discarded."""
         idx = indices.to(torch.int64).contiguous()
-        self._native.start_epoch(idx.data_ptr(), idx.numel(), int(num_batches))
+        nb = int(num_batches)
+        armed = self._armed
+        self._armed = None
+        if armed is None or armed[1] != nb or armed[0].shape != idx.shape or not torch.equal(armed[0], idx):
+            self._native.start_epoch(idx.data_ptr(), idx.numel(), nb)
         pending = []            # (slot, event) whose H2D copy may still be in flight
         while True:
             slot, rows = self._native.next()
@@ -64,3 +74,9 @@ class PinnedGatherLoader:
         for s, e in pending:
             e.synchronize()
             self._native.release(s)
+        if next_epoch is not None:
+            nxt = next_epoch()
+            if nxt is not None:
+                nidx = nxt[0].to(torch.int64).contiguous()
+                self._native.start_epoch(nidx.data_ptr(), nidx.numel(), int(nxt[1]))      # workers start filling slots now
+                self._armed = (nidx, int(nxt[1]))

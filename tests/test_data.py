@@ -78,3 +78,36 @@ def test_native_threaded_loader_matches_indexing():
             imgs.append(img.clone()); lbls.append(lbl.clone()); sizes.append(img.shape[0])
         assert sizes == [256] * (nb - 1) + [len(idx) - 256 * (nb - 1)]
         assert torch.equal(torch.cat(imgs)[:, 0], data.images[idx]) and torch.equal(torch.cat(lbls), data.labels[idx])
+
+
+def test_native_loader_speculative_next_epoch_and_restart():
+    """The native gather loader starts the NEXT epoch's batches as soon as the current epoch's last batch is out; the
+    next call either adopts that work (same indices) or discards it (different indices) -- same batches either way."""
+    from ddpt_b200.ops import load_ext
+    if load_ext() is None:
+        pytest.skip("extension not built")
+    from ddpt_b200.ops.host_loader import PinnedGatherLoader
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (500, 28, 28), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 10, (500,), generator=g)
+    loader = PinnedGatherLoader(images, labels, 64, device=None, depth=4, threads=2)
+    perms = [torch.randperm(500, generator=g) for _ in range(4)]
+
+    def run(idx, nxt=None):
+        out = []
+        for img, lbl, _ in loader.epoch(idx, 8, (lambda: (nxt, 8)) if nxt is not None else None):
+            out.append((img.clone(), lbl.clone()))
+        return out
+
+    def check(batches, idx):
+        assert len(batches) == 8
+        for b, (img, lbl) in enumerate(batches):
+            sel = idx[b * 64:(b + 1) * 64]
+            assert torch.equal(img.view(-1, 28, 28), images[sel]) and torch.equal(lbl, labels[sel])
+
+    check(run(perms[0], perms[1]), perms[0])
+    gathered = loader._native.batches_gathered()
+    check(run(perms[1], perms[2]), perms[1])                  # adopted: no restart, the head of the epoch was already gathered
+    assert loader._native.batches_gathered() >= gathered + 8
+    check(run(perms[3]), perms[3])                            # speculation (perms[2]) discarded, fresh start
+    check(run(perms[0]), perms[0])
