@@ -235,31 +235,39 @@ twoshot_kernel(AllReduceArgs a) {
   // bandwidth is bytes-in-flight limited (blocks x 512 threads x kUnroll x 16 B x world loads).
   constexpr int kUnroll = MC ? 8 : (WIRE == kWireBF16 ? 2 : 4);     // peer-load variants hold fp32 accumulators (64-register budget)
 
+  const long long slice = a.numel / a.world;              // elements owned by each rank
   if (WIRE == kWireBF16) {
-    // phase A: cast my whole bucket into my 16-bit staging (local read 4 B/elem, local write 2 B/elem)
-    const float* mine = a.peer_bufs[a.rank] + a.offset;
-    unsigned char* stage = a.peer_scratch[a.rank] + kPushBytes + 2 * a.offset;
-    const long long nvec_all = a.numel >> 3;
-    for (long long i0 = tid; i0 < nvec_all; i0 += stride * 4) {
-      float4 lo[4], hi[4];
+    // phase A: cast my bucket into my 16-bit staging (local read 4 B/elem, local write 2 B/elem).  The barriers pair
+    // CTA b of every rank with CTA b of every other rank and nothing else, so CTA b must produce exactly the staging
+    // vectors that the owners' CTA b will read in phase B: for every slice, the same (tid + k * stride) index set that
+    // phase B walks.  (A first version cast the bucket with a flat grid-stride loop: a peer's CTA could then read
+    // vectors that a *different* local CTA had not written yet -- invisible in eager runs, wrong gradients by a factor
+    // of world x loss_scale under CUDA-graph replay, where co-running kernels delay CTAs.)
+    const long long nvec_slice = slice >> 3;
+#pragma unroll 1
+    for (int r = 0; r < a.world; ++r) {
+      const float* mine = a.peer_bufs[a.rank] + a.offset + (long long)r * slice;
+      unsigned char* stage = a.peer_scratch[a.rank] + kPushBytes + 2 * (a.offset + (long long)r * slice);
+      for (long long i0 = tid; i0 < nvec_slice; i0 += stride * 4) {
+        float4 lo[4], hi[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < nvec_all) {
-          lo[u] = ld_nc_f4(reinterpret_cast<const float4*>(mine + 8 * i));
-          hi[u] = ld_nc_f4(reinterpret_cast<const float4*>(mine + 8 * i + 4));
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec_slice) {
+            lo[u] = ld_nc_f4(reinterpret_cast<const float4*>(mine + 8 * i));
+            hi[u] = ld_nc_f4(reinterpret_cast<const float4*>(mine + 8 * i + 4));
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < nvec_all) *reinterpret_cast<uint4*>(stage + 16 * i) = pack8(lo[u], hi[u]);
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec_slice) *reinterpret_cast<uint4*>(stage + 16 * i) = pack8(lo[u], hi[u]);
+        }
       }
     }
   }
   cross_gpu_barrier(a, 0, e, false);                      // everyone's gradients (staging) for this bucket are complete
 
-  const long long slice = a.numel / a.world;              // elements owned by this rank
   if (WIRE == kWireBF16) {
     const long long nvec = slice >> 3;
     const long long base = kPushBytes + 2 * (a.offset + (long long)a.rank * slice);      // byte offset in scratch
@@ -390,25 +398,29 @@ twoshot_kernel(AllReduceArgs a) {
   if (any_bad && threadIdx.x == 0 && a.found_inf != nullptr) *a.found_inf = 1.0f;
 
   if (WIRE == kWireBF16) {
-    // phase C: expand the averaged 16-bit staging into my fp32 arena (local)
-    float* mine = a.peer_bufs[a.rank] + a.offset;
-    const unsigned char* stage = a.peer_scratch[a.rank] + kPushBytes + 2 * a.offset;
-    const long long nvec_all = a.numel >> 3;
-    for (long long i0 = tid; i0 < nvec_all; i0 += stride * 4) {
-      uint4 v[4];
+    // phase C: expand the averaged 16-bit staging into my fp32 arena (local).  Same CTA-consistent index sets as phase
+    // A: slice r's vectors (tid + k * stride) were stored by owner r's CTA b, the one this CTA just met at the barrier.
+    const long long nvec_slice = slice >> 3;
+#pragma unroll 1
+    for (int r = 0; r < a.world; ++r) {
+      float* mine = a.peer_bufs[a.rank] + a.offset + (long long)r * slice;
+      const unsigned char* stage = a.peer_scratch[a.rank] + kPushBytes + 2 * (a.offset + (long long)r * slice);
+      for (long long i0 = tid; i0 < nvec_slice; i0 += stride * 4) {
+        uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < nvec_all) v[u] = ld_u4(stage + 16 * i);
-      }
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec_slice) v[u] = ld_u4(stage + 16 * i);
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < nvec_all) {
-          float4 lo, hi;
-          unpack8(v[u], lo, hi);
-          *reinterpret_cast<float4*>(mine + 8 * i) = lo;
-          *reinterpret_cast<float4*>(mine + 8 * i + 4) = hi;
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < nvec_slice) {
+            float4 lo, hi;
+            unpack8(v[u], lo, hi);
+            *reinterpret_cast<float4*>(mine + 8 * i) = lo;
+            *reinterpret_cast<float4*>(mine + 8 * i + 4) = hi;
+          }
         }
       }
     }

@@ -416,3 +416,48 @@ def _graphed_generic_ddp(rank, world):
 def test_graphed_train_step_with_ddp_hooks_world2():
     _need_gpus(2)
     run_gpu_ranks(_graphed_generic_ddp, 2)
+
+
+def _bf16_wire_under_graph(rank, world):
+    """Regression: the bf16 wire's cast / expand phases must use the same CTA-to-vector mapping as the reduce phase (the
+    barriers only pair CTA b with CTA b).  The first version passed every eager test and produced gradients off by
+    world x loss_scale under CUDA-graph replay, where co-running kernels delay individual CTAs."""
+    import torch.nn as nn
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.parallel import DistributedDataParallel as DDP
+    from ddpt_b200.utils import same_seeds
+    dev = torch.device("cuda", rank)
+    grads = {}
+    for wire in ("fp32", "bf16"):
+        amp.reset(); same_seeds(3)
+        model = Toy_Net().to(dev)
+        opt = Lookahead(SGD(model.parameters(), lr=0.0, momentum=0.9, nesterov=True), k=10, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level="O1")
+        ddp = DDP(model, device_ids=[rank], comm="fused", comm_wire=wire)
+        assert ops.attach_step_engine(ddp, nn.CrossEntropyLoss(), opt)
+        eng = ddp._ddpt_step_engine
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        x = torch.randint(0, 256, (1024, 1, 28, 28), device=dev, generator=g, dtype=torch.uint8)
+        y = torch.randint(0, 10, (1024,), device=dev, generator=g)
+        ddp.train(); eng.begin_pass()
+        for it in range(6):                                   # eager, capture + replay, 4 more replays
+            eng.run(x, y, True)
+            torch.cuda.synchronize()
+            grads[(wire, it)] = ddp.arena.grad_arena.clone()
+        assert eng.graph_replays >= 5
+    worst = 0.0
+    for it in range(6):
+        for bk in ddp.buckets:
+            a = grads[("fp32", it)][bk.start:bk.start + bk.numel]
+            b = grads[("bf16", it)][bk.start:bk.start + bk.numel]
+            rel = float((b - a).norm() / a.norm().clamp_min(1e-30))
+            assert rel < 2e-2, f"iter {it} bucket {bk.index}: bf16-wire gradients differ from fp32-wire by {rel:.3e}"
+            worst = max(worst, rel)
+    return worst
+
+
+def test_bf16_wire_matches_fp32_wire_under_graph_replay():
+    _need_gpus(2)
+    print("max relative gradient difference bf16 vs fp32 wire:", run_gpu_ranks(_bf16_wire_under_graph, 2))
