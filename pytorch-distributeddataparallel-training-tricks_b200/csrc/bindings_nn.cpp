@@ -41,7 +41,9 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
                                 bias.data_ptr<float>(), bfm(y), part, accum, batch, cur());
 }
 
-void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10::optional<at::Tensor> partials) {
+void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10::optional<at::Tensor> partials,
+                 c10::optional<at::Tensor> bn_y, c10::optional<at::Tensor> bn_g, c10::optional<at::Tensor> bn_coeffs,
+                 c10::optional<at::Tensor> bn_bwd_coef) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
   need(dy, at::kBFloat16, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
   const int batch = (int)(x.numel() / (28 * 28));
@@ -53,8 +55,17 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
     TORCH_CHECK(partials->numel() >= (int64_t)ddpt::conv0_wgrad_partial_rows() * 640, "conv0_wgrad: partials too small");
     part = partials->data_ptr<float>();
   }
+  ddpt::Conv0BnFuse bn{};
+  if (bn_y.has_value()) {         // fused BatchNorm-backward apply: dy is derived from (y0, g) on the fly
+    TORCH_CHECK(bn_g.has_value() && bn_coeffs.has_value() && bn_bwd_coef.has_value());
+    need(*bn_y, at::kBFloat16, "bn_y"); need(*bn_g, at::kBFloat16, "bn_g");
+    need(*bn_coeffs, at::kFloat, "bn_coeffs"); need(*bn_bwd_coef, at::kFloat, "bn_bwd_coef");
+    TORCH_CHECK(bn_y->numel() == dy.numel() && bn_g->numel() == dy.numel() && bn_coeffs->numel() >= 4 * 64 && bn_bwd_coef->numel() >= 3 * 64);
+    const float* co = bn_coeffs->data_ptr<float>();
+    bn = ddpt::Conv0BnFuse{bf(*bn_y), bf(*bn_g), co, co + 64, co + 128, co + 192, bn_bwd_coef->data_ptr<float>()};
+  }
   ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
-                           db.data_ptr<float>(), part, batch, cur());
+                           db.data_ptr<float>(), part, batch, bn, cur());
 }
 
 // coeffs: float [4][C] = scale, shift, mean, invstd
@@ -294,7 +305,9 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("conv0_partial_rows", &conv0_partial_rows);
   m.def("bn_bwd_partial_rows", &bn_bwd_partial_rows);
   m.def("conv0_fwd", &conv0_fwd);
-  m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none());
+  m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none(),
+        py::arg("bn_y") = py::none(), py::arg("bn_g") = py::none(), py::arg("bn_coeffs") = py::none(),
+        py::arg("bn_bwd_coef") = py::none());
   m.def("transpose_taps", &transpose_taps);
   m.def("det_workspace_floats", []() {     // fp32 elements of the deterministic-mode partial-row workspace
     return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,

@@ -20,9 +20,18 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/
 // dW [64][9], db [64] accumulated with atomics into zero-initialised (or beta=1) fp32 buffers.
 // partials (optional, [conv0_wgrad_partial_rows()][640] fp32): deterministic mode -- every block writes one row and an
 // ordered reduction kernel folds them into dw / db instead of global float atomics.
+// bn (optional): fold block 0's BatchNorm-backward apply into this kernel -- dy is computed from the saved BatchNorm input
+// y0, the incoming gradient g and the finalize coefficients instead of being read (conv.0 has no data gradient, so
+// nothing else needs dy0: the apply pass and its 88 MB write + read disappear).
+struct Conv0BnFuse {
+  const __nv_bfloat16* y;      // null: read dy
+  const __nv_bfloat16* g;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* bcoef;          // [3][64] from bn_bwd_finalize
+};
 int conv0_wgrad_partial_rows();
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
-                        int batch, cudaStream_t s);
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s);
 
 // ---- BatchNorm (training) ---------------------------------------------------------------------------
 struct BnCoeffs {          // all float [C]

@@ -155,12 +155,29 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
 
 __global__ void __launch_bounds__(kThreads)
 conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16* __restrict__ dy,
-                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ partials, int batch) {
+                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ partials, int batch,
+                   const Conv0BnFuse bn) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ float s_img[kImg * kImg];
   __shared__ float s_acc[kThreads / 32][kC0 * 10];         // one slot per warp: ordered block fold
   const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  // BatchNorm-backward "apply" of block 0 folded in: conv.0 has no data gradient, so dy0 is read exactly once -- here.
+  // Instead of a pass that reads y0 and g and writes dy0 (88 MB) for this kernel to read back, compute
+  // dy = c1 * dz + k0 - k1 * y (dz = g where relu(bn(y)) > 0) from y0 and g directly, rounded to bf16 like the stored one.
+  const bool fused = bn.y != nullptr;
+  float f_sc[8], f_sh[8], f_c1[8], f_k0[8], f_k1[8];
+  if (fused) {
+    float mu[8], is[8], c2[8], c3[8];
+    load8f(bn.scale + cg * 8, f_sc); load8f(bn.shift + cg * 8, f_sh);
+    load8f(bn.mean + cg * 8, mu); load8f(bn.invstd + cg * 8, is);
+    load8f(bn.bcoef + cg * 8, f_c1); load8f(bn.bcoef + kC0 + cg * 8, c2); load8f(bn.bcoef + 2 * kC0 + cg * 8, c3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f_k1[j] = f_c1[j] * is[j] * c3[j];
+      f_k0[j] = fmaf(f_k1[j], mu[j], -f_c1[j] * c2[j]);
+    }
+  }
   float acc[8][10];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -172,11 +189,15 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
     __syncthreads();
     constexpr int kStep = kThreads / 8;                      // 32 pixels per sweep of the block
     for (int p0 = prow; p0 < kPix0; p0 += 4 * kStep) {
-      uint4 raw[4];                                          // four gradient vectors in flight per thread
+      uint4 raw[4], rawy[4];                                 // four gradient vectors in flight per thread
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int p = p0 + u * kStep;
-        if (p < kPix0) raw[u] = ldg16(dy + ((size_t)img * kPix0 + p) * kC0 + cg * 8);
+        if (p < kPix0) {
+          const size_t off = ((size_t)img * kPix0 + p) * kC0 + cg * 8;
+          if (fused) { raw[u] = ldg16(bn.g + off); rawy[u] = ldg16(bn.y + off); }
+          else raw[u] = ldg16(dy + off);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -185,6 +206,15 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
         const int oh = p / kOut0, ow = p - oh * kOut0;
         float g[8];
         unpack8(raw[u], g);
+        if (fused) {
+          float yv[8];
+          unpack8(rawy[u], yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dz = fmaf(yv[j], f_sc[j], f_sh[j]) > 0.f ? g[j] : 0.f;
+            g[j] = __bfloat162float(__float2bfloat16(fmaf(f_c1[j], dz, fmaf(-f_k1[j], yv[j], f_k0[j]))));
+          }
+        }
         float in[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -1128,9 +1158,11 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const floa
 int conv0_wgrad_partial_rows() { return sm_count() * 2; }
 
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
-                        int batch, cudaStream_t s) {
-  const int grid = batch < sm_count() * 2 ? batch : sm_count() * 2;
-  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, partials, batch);
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s) {
+  // the fused variant holds 40 more per-thread constants (177 registers): one resident CTA per SM, so one CTA per SM
+  const int per_sm = bn.y != nullptr ? 1 : 2;
+  const int grid = batch < sm_count() * per_sm ? batch : sm_count() * per_sm;
+  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, partials, batch, bn);
   if (partials != nullptr) {          // deterministic mode: fold the block rows in order (dw: 576 columns, db: 64)
     launch_pdl(reduce_rows_kernel, dim3((kC0 * 9 + kThreads - 1) / kThreads), dim3(kThreads), 0, s,
                (const float*)partials, grid, kC0 * 10, kC0 * 9, dw, 1);

@@ -110,6 +110,7 @@ class FusedToyNet:
         self.deterministic = deterministic()
         self._det_ws: Optional[torch.Tensor] = None
         self.dgrad64_pair = os.environ.get("DDPT_DGRAD64_PAIR", "0") == "1"
+        self.fuse_conv0_bn = os.environ.get("DDPT_FUSE_CONV0_BN", "1") != "0"
         self.dense_splitk = int(os.environ.get("DDPT_DENSE_SPLITK", "4"))   # measured: 128 x 128 tiles x 4 splits 27.5 us, 64-wide tiles unsplit 35.8 us
         self.fused_stats = (compute != "fp8" and not deterministic()
                             and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
@@ -119,6 +120,8 @@ class FusedToyNet:
         fwd = 1 + 1 + 1 + 3 * 3 + 3              # conv0, finalize, apply | 3x(conv, finalize, apply) | dense.1 trio (head: in bwd)
         bwd = 1 + 3 + 2 + 3 * (3 + 2) + 3 + 1    # head | bn1d x3 | dense.1 wgrad+dgrad | 3x(bn x3, wgrad, dgrad) | bn0 x3 | conv0 wgrad
         bwd += 1 + 2                             # flatten -> channels-last transpose | split-K slab reductions (conv.3, conv.10 wgrad)
+        if self.fuse_conv0_bn and not self.fused_stats:
+            bwd -= 1                             # block 0's bn_bwd_apply lives in conv0_wgrad
         if self.dense_splitk > 1 and not self.fused_stats and batch >= 256 and self.compute != "fp8":
             fwd += 1                             # dense.1: split-K GEMM + slab fold / statistics pass
         if self.fused_stats:
@@ -326,9 +329,19 @@ class FusedToyNet:
             if c_in == 64 and self.dgrad64_pair:     # conv.3 on CTA pairs needs the K-major (tap-transposed) weights
                 w_t = gemm.transpose_taps(self._weight_bf16(pidx), 9, ws.wt3)
             g = gemm.conv_dgrad(ws.dy[k], self._weight_bf16(pidx), 3, 3, ws.da[k - 1], w_t=w_t)
-        self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
-        ready(3); ready(2)
-        ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1], self.det_partials())
+        if self.fuse_conv0_bn and not self.fused_stats:
+            # block 0: conv.0 has no data gradient, so dy0 would be written by the BatchNorm apply pass only for
+            # conv.0's weight gradient to read back.  Reduce + finalize as usual; the apply folds into conv0_wgrad.
+            bn0 = self.bn[0]
+            rows = ext.bn_bwd_reduce(ws.y[0], g, ws.coef[0], ws.part, False, False)
+            ext.bn_bwd_finalize(ws.part, rows, batch * 676.0, bn0.weight, ws.coef[0], grads[2], grads[3], ws.bcoef[0], False)
+            ready(3); ready(2)
+            ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1], self.det_partials(), ws.y[0], g, ws.coef[0],
+                            ws.bcoef[0])
+        else:
+            self._bn_backward(0, ws, g, grads, False, False, batch * 676.0, dbias_idx=None)
+            ready(3); ready(2)
+            ext.conv0_wgrad(x, ws.dy[0], grads[0].view(-1), grads[1], self.det_partials())
         if side_stream is not None:                       # join: everything after backward sees all weight gradients
             ev = torch.cuda.Event()
             ev.record(side_stream)
