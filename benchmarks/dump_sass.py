@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "pytorch-distributeddataparallel-training-tricks_b200", "_ext", "obj")
 OUT = os.path.join(ROOT, "sass")
 KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "LDGMC", "STGMC",
-       "REDG", "ATOMG", "HMMA", "LDGSTS", "SHFL", "LDG", "STG", "BAR"]
+       "MEMBAR", "REDG", "ATOMG", "HMMA", "LDGSTS", "SHFL", "LDG", "STG", "ST", "LD", "BAR"]
 os.makedirs(OUT, exist_ok=True)
 rows = []
 for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.*.o"))):
@@ -26,9 +26,11 @@ for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.*.o"))):
             found["*.2CTA"] = pair
         pdl = sum(1 for o in ops if o.startswith("ACQBULK") or o.startswith("PREEXIT"))
         rows.append((src, short, len(ops), found))
-        keep = ("conv_gemm_persistent_kernel<256, false, false, 2>", "conv_gemm_halo_kernel<128, false, true>",
+        keep = ("conv_gemm_persistent_kernel<256, false, false, 2>", "conv_gemm_persistent_kernel<256, true, false, 2>",
+                "conv_gemm_halo_kernel<128, false, true, 1, 1>", "conv_gemm_halo_kernel<64, true, true, 1, 2>",
                 "wgrad_gemm_kernel<128>", "wgrad_multitap_kernel<64, 256>", "conv_gemm_mxfp8_kernel",
-                "fused_allreduce_kernel<3>", "fused_allreduce_kernel<2>", "fused_lookahead_sgd_kernel")
+                "twoshot_kernel<0, true>", "twoshot_kernel<1, true>", "twoshot_kernel<0, false>",
+                "oneshot_push_kernel<0, true>", "symm_broadcast_kernel<true>", "fused_lookahead_sgd_kernel")
         if short in keep:     # full listings only for one representative of every kernel family (the rest: SUMMARY.md)
             fn = re.sub(r"[^A-Za-z0-9_]+", "_", short)[:80]
             with open(os.path.join(OUT, fn + ".sass"), "w") as fh:
@@ -37,7 +39,8 @@ with open(os.path.join(OUT, "SUMMARY.md"), "w") as fh:
     fh.write("# SASS evidence (cuobjdump -sass of the in-tree sm_100a objects)\n\n"
              "`UTCHMMA` = tcgen05.mma (kind::f16), `UTMALDG` = TMA tensor load, `LDTM` = tcgen05.ld, "
              "`UTCBAR` = tcgen05.commit, `UTCATOMSWS` = TMEM alloc, `SYNCS` = mbarrier ops, "
-             "`LDGMC` = multimem.ld_reduce, `REDG` = red.global, `ATOMG` = system-scope CAS flags, "
+             "`LDGMC` = multimem.ld_reduce (`LDGMC.E.ADD.F32` fp32 wire, `LDGMC.E.HPADD.BF16` bf16 wire with fp32 accumulation), "
+             "`MEMBAR` + `ST`/`LD` with .SYS = the release / acquire flag barrier, `REDG` = red.global, "
              "`*.2CTA` = cta_group::2 forms (paired MMA, pair TMA loads, multicast commit, pair TMEM alloc).\n\n"
              "| source | kernel | SASS instrs | key mnemonics |\n|---|---|---|---|\n")
     for src, short, n, c in rows:
