@@ -101,9 +101,11 @@ void fused_lookahead_sgd(at::Tensor params, at::Tensor grads, at::Tensor momentu
   a.momentum = momentum.data_ptr<float>();
   a.slow = slow.has_value() ? slow->data_ptr<float>() : nullptr;
   if (shadow.has_value()) {
-    check_cuda(*shadow, "shadow", at::kBFloat16);
+    TORCH_CHECK(shadow->is_cuda() && (shadow->scalar_type() == at::kBFloat16 || shadow->scalar_type() == at::kHalf),
+                "shadow must be a CUDA bf16 or fp16 tensor");
     TORCH_CHECK(shadow->numel() == params.numel());
     a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow->data_ptr());
+    a.shadow_fp16 = shadow->scalar_type() == at::kHalf ? 1 : 0;
   }
   a.grads_to_zero = zero_grads ? grads.data_ptr<float>() : nullptr;
   a.hyper = hyper.data_ptr<float>();
@@ -115,11 +117,12 @@ void fused_lookahead_sgd(at::Tensor params, at::Tensor grads, at::Tensor momentu
 }
 
 void cast_bf16(at::Tensor src, at::Tensor dst) {
-  check_cuda(src, "src", at::kFloat); check_cuda(dst, "dst", at::kBFloat16);
+  check_cuda(src, "src", at::kFloat);
+  TORCH_CHECK(dst.is_cuda() && (dst.scalar_type() == at::kBFloat16 || dst.scalar_type() == at::kHalf));
   TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && src.numel() == dst.numel() && src.numel() % 4 == 0);
   c10::cuda::CUDAGuard guard(src.device());
   ddpt::launch_cast_bf16(src.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()), src.numel(),
-                         current_stream());
+                         current_stream(), dst.scalar_type() == at::kHalf ? 1 : 0);
 }
 
 // ---- tensor-core GEMM / conv ----------------------------------------------------------------------
@@ -129,10 +132,12 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
                   std::vector<int64_t> a_off_hw, bool b_mn_major, c10::optional<at::Tensor> bias, bool relu,
                   c10::optional<at::Tensor> stat_partials, int64_t split_k, int64_t block_n, int64_t mode,
                   bool split_slabs) {
-  check_cuda(a, "a", at::kBFloat16); check_cuda(b, "b", at::kBFloat16);
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && (a.scalar_type() == at::kBFloat16 || a.scalar_type() == at::kHalf) &&
+              b.scalar_type() == a.scalar_type(), "a and b must be CUDA tensors of the same 16-bit type (bf16 or fp16)");
   TORCH_CHECK(a.dim() == 4 && a.is_contiguous(), "a must be contiguous [N,H,W,C]");
   TORCH_CHECK(b.dim() == 2 && b.stride(1) == 1, "b must be 2-D with unit inner stride");
-  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && (out.scalar_type() == at::kBFloat16 || out.scalar_type() == at::kFloat));
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && (out.scalar_type() == a.scalar_type() || out.scalar_type() == at::kFloat),
+              "out must be fp32 or the operands' 16-bit type");
   c10::cuda::CUDAGuard guard(a.device());
   ddpt::ConvGemmProblem p{};
   p.a = reinterpret_cast<const __nv_bfloat16*>(a.data_ptr());
@@ -144,6 +149,7 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
   p.b = reinterpret_cast<const __nv_bfloat16*>(b.data_ptr());
   p.b_mn_major = b_mn_major ? 1 : 0;
   p.b_ld = b.stride(0);
+  p.fp16 = a.scalar_type() == at::kHalf ? 1 : 0;
   const int64_t taps = p.taps_h * p.taps_w;
   if (b_mn_major) {
     TORCH_CHECK(b.size(0) == p.a_c && b.size(1) % taps == 0, "MN-major b must be [C_k, taps*N]");
@@ -193,7 +199,9 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
 void wgrad_gemm(at::Tensor dy, at::Tensor x, at::Tensor dw, std::vector<int64_t> taps_hw,
                 std::vector<int64_t> box_nhw, int64_t split_k, bool accumulate, int64_t block_n, bool multitap,
                 c10::optional<at::Tensor> slab) {
-  check_cuda(dy, "dy", at::kBFloat16); check_cuda(x, "x", at::kBFloat16); check_cuda(dw, "dw", at::kFloat);
+  TORCH_CHECK(dy.is_cuda() && x.is_cuda() && (dy.scalar_type() == at::kBFloat16 || dy.scalar_type() == at::kHalf) &&
+              x.scalar_type() == dy.scalar_type(), "dy and x must be CUDA tensors of the same 16-bit type");
+  check_cuda(dw, "dw", at::kFloat);
   TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous() && x.dim() == 4 && x.is_contiguous() && dw.is_contiguous());
   TORCH_CHECK(dy.size(0) == x.size(0));
   c10::cuda::CUDAGuard guard(dy.device());
@@ -204,6 +212,7 @@ void wgrad_gemm(at::Tensor dy, at::Tensor x, at::Tensor dw, std::vector<int64_t>
   p.in_h = (int)x.size(1); p.in_w = (int)x.size(2); p.c_total = (int)x.size(3);
   p.taps_h = (int)taps_hw[0]; p.taps_w = (int)taps_hw[1];
   p.box_n = (int)box_nhw[0]; p.box_h = (int)box_nhw[1]; p.box_w = (int)box_nhw[2];
+  p.fp16 = dy.scalar_type() == at::kHalf ? 1 : 0;
   TORCH_CHECK(dw.numel() == (int64_t)p.m_total * p.taps_h * p.taps_w * p.c_total, "dw has the wrong size");
   p.dw = dw.data_ptr<float>();
   p.split_k = (int)split_k; p.accumulate = accumulate ? 1 : 0;
@@ -232,7 +241,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("split_slabs") = false);
   m.def("splitk_finish", [](at::Tensor slabs, int64_t splits, at::Tensor out, c10::optional<at::Tensor> stat_partials) {
     TORCH_CHECK(slabs.is_cuda() && slabs.scalar_type() == at::kFloat && slabs.is_contiguous() && slabs.dim() == 2);
-    TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.is_contiguous() && out.dim() == 2);
+    TORCH_CHECK(out.is_cuda() && (out.scalar_type() == at::kBFloat16 || out.scalar_type() == at::kHalf) && out.is_contiguous() && out.dim() == 2);
     const int64_t rows = out.size(0), cols = out.size(1);
     TORCH_CHECK(slabs.size(0) == splits * rows && slabs.size(1) == cols, "slabs must be [splits * rows, cols]");
     float* part = nullptr;
@@ -242,7 +251,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     }
     c10::cuda::CUDAGuard guard(out.device());
     return (int64_t)ddpt::launch_splitk_finish(slabs.data_ptr<float>(), (int)splits, rows * cols, (int)rows, (int)cols,
-                                               reinterpret_cast<__nv_bfloat16*>(out.data_ptr()), part, current_stream());
+                                               reinterpret_cast<__nv_bfloat16*>(out.data_ptr()), part,
+                                               out.scalar_type() == at::kHalf ? 1 : 0, current_stream());
   });
   m.def("wgrad_gemm", &wgrad_gemm);
   ddpt_bind_extra(m);

@@ -3,6 +3,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <cuda_fp16.h>
 #include "include/ddpt_toynet.h"
 #include "include/ddpt_fp8.h"
 
@@ -15,6 +16,14 @@ __nv_bfloat16* bfm(at::Tensor& t) { return reinterpret_cast<__nv_bfloat16*>(t.da
 void need(const at::Tensor& t, at::ScalarType dt, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.scalar_type() == dt && t.is_contiguous(), name, ": expected contiguous CUDA ", dt);
 }
+// activations are bf16 (O1) or fp16 (O1-fp16); every activation tensor of one call must have the same type
+bool is_half(const at::Tensor& t) { return t.scalar_type() == at::kHalf; }
+void need_act(const at::Tensor& t, const at::Tensor& like, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && (t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kHalf) &&
+              t.scalar_type() == like.scalar_type(), name, ": expected a contiguous CUDA bf16 / fp16 tensor (all of one type)");
+}
+const __half* hf(const at::Tensor& t) { return reinterpret_cast<const __half*>(t.data_ptr()); }
+__half* hfm(at::Tensor& t) { return reinterpret_cast<__half*>(t.data_ptr()); }
 
 int64_t conv0_partial_rows() { return ddpt::conv0_partial_rows(); }
 int64_t bn_bwd_partial_rows() { return ddpt::bn_bwd_partial_rows(); }
@@ -22,7 +31,7 @@ int64_t bn_bwd_partial_rows() { return ddpt::bn_bwd_partial_rows(); }
 int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y, c10::optional<at::Tensor> partials) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
   TORCH_CHECK(x.numel() % (28 * 28) == 0, "conv0 expects 28x28 single-channel images");
-  need(weight, at::kFloat, "weight"); need(bias, at::kFloat, "bias"); need(y, at::kBFloat16, "y");
+  need(weight, at::kFloat, "weight"); need(bias, at::kFloat, "bias"); need_act(y, y, "y");
   const int batch = (int)(x.numel() / (28 * 28));
   TORCH_CHECK(weight.numel() == 64 * 9 && bias.numel() == 64 && y.numel() == (int64_t)batch * 26 * 26 * 64);
   c10::cuda::CUDAGuard g(x.device());
@@ -37,6 +46,9 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
     TORCH_CHECK(partials->numel() >= ddpt::conv0_partial_rows() * 2 * 64);
     part = partials->data_ptr<float>();
   }
+  if (is_half(y))
+    return ddpt::launch_conv0_fwd(x.data_ptr(), x.scalar_type() == at::kByte, weight.data_ptr<float>(),
+                                  bias.data_ptr<float>(), hfm(y), part, accum, batch, cur());
   return ddpt::launch_conv0_fwd(x.data_ptr(), x.scalar_type() == at::kByte, weight.data_ptr<float>(),
                                 bias.data_ptr<float>(), bfm(y), part, accum, batch, cur());
 }
@@ -45,7 +57,7 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
                  c10::optional<at::Tensor> bn_y, c10::optional<at::Tensor> bn_g, c10::optional<at::Tensor> bn_coeffs,
                  c10::optional<at::Tensor> bn_bwd_coef) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
-  need(dy, at::kBFloat16, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
+  need_act(dy, dy, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
   const int batch = (int)(x.numel() / (28 * 28));
   TORCH_CHECK(dy.numel() == (int64_t)batch * 26 * 26 * 64 && dw.numel() == 576 && db.numel() == 64);
   c10::cuda::CUDAGuard g(x.device());
@@ -58,14 +70,18 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
   ddpt::Conv0BnFuse bn{};
   if (bn_y.has_value()) {         // fused BatchNorm-backward apply: dy is derived from (y0, g) on the fly
     TORCH_CHECK(bn_g.has_value() && bn_coeffs.has_value() && bn_bwd_coef.has_value());
-    need(*bn_y, at::kBFloat16, "bn_y"); need(*bn_g, at::kBFloat16, "bn_g");
+    need_act(*bn_y, dy, "bn_y"); need_act(*bn_g, dy, "bn_g");
     need(*bn_coeffs, at::kFloat, "bn_coeffs"); need(*bn_bwd_coef, at::kFloat, "bn_bwd_coef");
     TORCH_CHECK(bn_y->numel() == dy.numel() && bn_g->numel() == dy.numel() && bn_coeffs->numel() >= 4 * 64 && bn_bwd_coef->numel() >= 3 * 64);
     const float* co = bn_coeffs->data_ptr<float>();
-    bn = ddpt::Conv0BnFuse{bf(*bn_y), bf(*bn_g), co, co + 64, co + 128, co + 192, bn_bwd_coef->data_ptr<float>()};
+    bn = ddpt::Conv0BnFuse{bn_y->data_ptr(), bn_g->data_ptr(), co, co + 64, co + 128, co + 192, bn_bwd_coef->data_ptr<float>()};
   }
-  ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
-                           db.data_ptr<float>(), part, batch, bn, cur());
+  if (is_half(dy))
+    ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, hf(dy), dw.data_ptr<float>(),
+                             db.data_ptr<float>(), part, batch, bn, cur());
+  else
+    ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
+                             db.data_ptr<float>(), part, batch, bn, cur());
 }
 
 // coeffs: float [4][C] = scale, shift, mean, invstd
@@ -107,7 +123,7 @@ void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bo
                   c10::optional<at::Tensor> beta, double eps, double momentum,
                   c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
                   c10::optional<at::Tensor> nbt) {
-  need(y, at::kBFloat16, "y"); need(coeffs, at::kFloat, "coeffs"); need(out, at::kBFloat16, "out");
+  need_act(y, y, "y"); need(coeffs, at::kFloat, "coeffs"); need_act(out, y, "out");
   TORCH_CHECK(y.dim() == 4);
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(out.numel() == (pool ? y.numel() / 4 : y.numel()));
@@ -137,18 +153,20 @@ void bn_relu_pool(at::Tensor y, at::Tensor coeffs, at::Tensor out, bool pool, bo
     }
     if (nbt.has_value()) { TORCH_CHECK(nbt->scalar_type() == at::kLong); f.num_batches_tracked = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
   }
-  ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, f, cur());
+  if (is_half(y)) ddpt::launch_bn_relu_pool(hf(y), co, co + c, hfm(out), n, h, w, c, pool, flatten_chw, qd, qs, f, cur());
+  else ddpt::launch_bn_relu_pool(bf(y), co, co + c, bfm(out), n, h, w, c, pool, flatten_chw, qd, qs, f, cur());
 }
 
 void chw_to_hwc(at::Tensor in, at::Tensor out, int64_t c, int64_t p) {
-  need(in, at::kBFloat16, "in"); need(out, at::kBFloat16, "out");
+  need_act(in, in, "in"); need_act(out, in, "out");
   TORCH_CHECK(in.numel() == out.numel() && in.numel() % (c * p) == 0, "chw_to_hwc: [N, C*P] -> [N, P, C]");
   c10::cuda::CUDAGuard g(in.device());
-  ddpt::launch_chw_to_hwc(bf(in), bfm(out), (int)(in.numel() / (c * p)), (int)c, (int)p, cur());
+  if (is_half(in)) ddpt::launch_chw_to_hwc(hf(in), hfm(out), (int)(in.numel() / (c * p)), (int)c, (int)p, cur());
+  else ddpt::launch_chw_to_hwc(bf(in), bfm(out), (int)(in.numel() / (c * p)), (int)c, (int)p, cur());
 }
 
 int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor partials, bool pool, bool flatten_chw) {
-  need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
+  need_act(y, y, "y"); need_act(g_in, y, "g"); need(coeffs, at::kFloat, "coeffs");
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(g_in.numel() == (pool ? y.numel() / 4 : y.numel()));
   float* part = nullptr; double* accum = nullptr;
@@ -162,6 +180,9 @@ int64_t bn_bwd_reduce(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tens
   }
   c10::cuda::CUDAGuard guard(y.device());
   const float* co = coeffs.data_ptr<float>();
+  if (is_half(y))
+    return ddpt::launch_bn_bwd_reduce(hf(y), hf(g_in), co, co + c, co + 2 * c, co + 3 * c, part, accum, n,
+                                      h, w, c, pool, flatten_chw, cur());
   return ddpt::launch_bn_bwd_reduce(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, part, accum, n,
                                     h, w, c, pool, flatten_chw, cur());
 }
@@ -185,8 +206,8 @@ void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor b
                   c10::optional<at::Tensor> dbias, bool pool, bool flatten_chw, c10::optional<at::Tensor> accum,
                   double count, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> dgamma,
                   c10::optional<at::Tensor> dbeta) {
-  need(y, at::kBFloat16, "y"); need(g_in, at::kBFloat16, "g"); need(coeffs, at::kFloat, "coeffs");
-  need(bwd_coef, at::kFloat, "bwd_coef"); need(dy, at::kBFloat16, "dy");
+  need_act(y, y, "y"); need_act(g_in, y, "g"); need(coeffs, at::kFloat, "coeffs");
+  need(bwd_coef, at::kFloat, "bwd_coef"); need_act(dy, y, "dy");
   const int n = (int)y.size(0), h = (int)y.size(1), w = (int)y.size(2), c = (int)y.size(3);
   TORCH_CHECK(dy.numel() == y.numel());
   c10::cuda::CUDAGuard guard(y.device());
@@ -202,16 +223,21 @@ void bn_bwd_apply(at::Tensor y, at::Tensor g_in, at::Tensor coeffs, at::Tensor b
     f.accum = accum->data_ptr<double>(); f.count = count; f.inv_count = 1.0 / count; f.gamma = gamma->data_ptr<float>();
     f.dgamma = dgamma->data_ptr<float>(); f.dbeta = dbeta->data_ptr<float>();
   }
-  ddpt::launch_bn_bwd_apply(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, bwd_coef.data_ptr<float>(), bfm(dy), db,
-                            f, n, h, w, c, pool, flatten_chw, cur());
+  if (is_half(y))
+    ddpt::launch_bn_bwd_apply(hf(y), hf(g_in), co, co + c, co + 2 * c, co + 3 * c, bwd_coef.data_ptr<float>(), hfm(dy), db,
+                              f, n, h, w, c, pool, flatten_chw, cur());
+  else
+    ddpt::launch_bn_bwd_apply(bf(y), bf(g_in), co, co + c, co + 2 * c, co + 3 * c, bwd_coef.data_ptr<float>(), bfm(dy), db,
+                              f, n, h, w, c, pool, flatten_chw, cur());
 }
 
 void transpose_taps(at::Tensor w, at::Tensor wt, int64_t taps) {
-  need(w, at::kBFloat16, "w"); need(wt, at::kBFloat16, "wt");
+  need_act(w, w, "w"); need_act(wt, w, "wt");
   TORCH_CHECK(w.dim() == 2 && wt.dim() == 2 && w.numel() == wt.numel() && w.size(1) % taps == 0 && wt.size(1) == taps * w.size(0),
               "transpose_taps: w [c_out, taps*c_in] -> wt [c_in, taps*c_out]");
   c10::cuda::CUDAGuard g(w.device());
-  ddpt::launch_transpose_taps(bf(w), bfm(wt), (int)w.size(0), (int)taps, (int)(w.size(1) / taps), cur());
+  if (is_half(w)) ddpt::launch_transpose_taps(hf(w), hfm(wt), (int)w.size(0), (int)taps, (int)(w.size(1) / taps), cur());
+  else ddpt::launch_transpose_taps(bf(w), bfm(wt), (int)w.size(0), (int)taps, (int)(w.size(1) / taps), cur());
 }
 
 // Forward-only when da is None.  dlogits: if given, used instead of the fused cross-entropy gradient.
@@ -219,11 +245,11 @@ void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> ta
           c10::optional<at::Tensor> metrics, c10::optional<at::Tensor> loss_scale, c10::optional<at::Tensor> da,
           c10::optional<at::Tensor> dw, c10::optional<at::Tensor> db, c10::optional<at::Tensor> dlogits,
           double extra_div, c10::optional<at::Tensor> partials) {
-  need(a, at::kBFloat16, "a"); need(w, at::kFloat, "w"); need(b, at::kFloat, "b");
+  need_act(a, a, "a"); need(w, at::kFloat, "w"); need(b, at::kFloat, "b");
   TORCH_CHECK(a.dim() == 2 && a.size(1) == 512 && w.numel() == 5120 && b.numel() == 10);
   c10::cuda::CUDAGuard guard(a.device());
   ddpt::HeadArgs h{};
-  h.a = bf(a); h.w = w.data_ptr<float>(); h.b = b.data_ptr<float>(); h.batch = (int)a.size(0);
+  h.a = a.data_ptr(); h.w = w.data_ptr<float>(); h.b = b.data_ptr<float>(); h.batch = (int)a.size(0);
   if (target.has_value()) { TORCH_CHECK(target->scalar_type() == at::kLong && target->numel() == h.batch);
     h.target = reinterpret_cast<const long long*>(target->data_ptr<int64_t>()); }
   if (logits.has_value()) { need(*logits, at::kFloat, "logits"); h.logits = logits->data_ptr<float>(); }
@@ -231,8 +257,8 @@ void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> ta
   if (loss_scale.has_value()) h.loss_scale = loss_scale->data_ptr<float>();
   if (da.has_value()) {
     TORCH_CHECK(dw.has_value() && db.has_value());
-    need(*da, at::kBFloat16, "da"); need(*dw, at::kFloat, "dw"); need(*db, at::kFloat, "db");
-    h.da = bfm(*da); h.dw = dw->data_ptr<float>(); h.db = db->data_ptr<float>();
+    need_act(*da, a, "da"); need(*dw, at::kFloat, "dw"); need(*db, at::kFloat, "db");
+    h.da = da->data_ptr(); h.dw = dw->data_ptr<float>(); h.db = db->data_ptr<float>();
   }
   if (dlogits.has_value()) { need(*dlogits, at::kFloat, "dlogits"); h.dlogits = dlogits->data_ptr<float>(); }
   TORCH_CHECK(h.target != nullptr || (h.metrics == nullptr && (h.da == nullptr || h.dlogits != nullptr)),
@@ -244,7 +270,8 @@ void head(at::Tensor a, at::Tensor w, at::Tensor b, c10::optional<at::Tensor> ta
                 "head: partials too small");
     h.partials = partials->data_ptr<float>();
   }
-  ddpt::launch_head(h, cur());
+  if (is_half(a)) ddpt::launch_head_f16(h, cur());
+  else ddpt::launch_head(h, cur());
 }
 
 // x: [rows, cols] bf16/fp32 contiguous (cols % 32 == 0) -> (uint8 e4m3 [rows, cols], uint8 UE8M0 [rows, cols/32])

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace ddpt {
@@ -68,6 +69,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 

@@ -42,6 +42,7 @@ struct ConvGemmProblem {
                                            // partial rows, and the consumer pass derives the BatchNorm coefficients itself
                                            // (no *_finalize launch).  Unordered adds: use stat_partials for bit-stable runs.
   int split_k;                             // K splits (fp32 output only)
+  int fp16;                                // A / B operands (and a 16-bit output) are fp16, not bf16: same layouts, other format
   long long split_slab_stride;             // > 0: split z stores its partial tile at out + z * stride (plain stores, no
                                            // atomics); splitk_finish folds the slabs in order (+ bf16 pack + BN statistics)
 };
@@ -59,7 +60,7 @@ int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t st
 // BatchNorm column statistics as partial rows [blocks][2][cols] (returns the number of rows written) -- the second half
 // of a split-K linear layer whose output tile grid alone cannot fill the GPU (Toy_Net dense.1: 64 tiles on 148 SMs).
 int launch_splitk_finish(const float* slabs, int splits, long long slab_stride, int rows, int cols,
-                         __nv_bfloat16* out, float* stat_partials, cudaStream_t stream);
+                         __nv_bfloat16* out, float* stat_partials, int fp16, cudaStream_t stream);
 int splitk_finish_max_rows();
 
 // Weight gradient: dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n]  (both operands MN-major,
@@ -74,6 +75,7 @@ struct WgradProblem {
   float* dw;                               // [M, taps_h, taps_w, C] fp32
   int split_k;                             // number of pixel-brick partitions (vector red.add when > 1)
   int accumulate;                          // 1: add into dw even when split_k == 1 (beta = 1)
+  int fp16;                                // dy / x are fp16 instead of bf16
   float* slab;                             // multitap only: optional [split_k][M*taps*C] fp32 workspace; partials are
                                            // stored there and folded by a reduction kernel instead of red.add
 };

@@ -17,7 +17,8 @@ struct FusedSgdArgs {
   const float* grads;            // fp32 gradients (arena, already unscaled)
   float* momentum;               // fp32 momentum buffers (arena)
   float* slow;                   // fp32 Lookahead slow weights (arena) or nullptr (no Lookahead)
-  __nv_bfloat16* shadow;         // optional bf16 copy of the weights for the tensor-core path
+  __nv_bfloat16* shadow;         // optional 16-bit copy of the weights for the tensor-core path
+  int shadow_fp16;               // 0: the shadow is bf16, 1: fp16 (O1-fp16)
   float* grads_to_zero;          // optional: zero the gradient arena after it has been consumed
   const float* hyper;            // float[kHyperSlots]
   int* state;                    // int[kOptStateSlots]
@@ -28,6 +29,6 @@ struct FusedSgdArgs {
 
 void launch_fused_lookahead_sgd(const FusedSgdArgs& args, cudaStream_t stream);
 // fp32 -> bf16 re-cast of an arena (used once at attach time and after load_state_dict).
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long numel, cudaStream_t stream);
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long numel, cudaStream_t stream, int fp16 = 0);
 
 }  // namespace ddpt

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace ddpt {
@@ -24,8 +25,8 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/
 // y0, the incoming gradient g and the finalize coefficients instead of being read (conv.0 has no data gradient, so
 // nothing else needs dy0: the apply pass and its 88 MB write + read disappear).
 struct Conv0BnFuse {
-  const __nv_bfloat16* y;      // null: read dy
-  const __nv_bfloat16* g;
+  const void* y;               // null: read dy (activation type of the overload called: bf16 or fp16)
+  const void* g;
   const float* scale; const float* shift; const float* mean; const float* invstd;
   const float* bcoef;          // [3][64] from bn_bwd_finalize
 };
@@ -100,7 +101,7 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
 
 // ---- classifier head: Linear(512,10) + CrossEntropy(mean)/B + argmax, forward and backward ------------------
 struct HeadArgs {
-  const __nv_bfloat16* a;      // [B,512] relu(bn(y4))
+  const void* a;               // [B,512] relu(bn(y4)); bf16 (launch_head) or fp16 (launch_head_f16)
   const float* w;              // [10,512] fp32 master weights
   const float* b;              // [10]
   const long long* target;     // [B]
@@ -109,7 +110,7 @@ struct HeadArgs {
   float* metrics;              // [2]: += sum_i CE_i / B   and  += #correct
   // training only (null in eval)
   const float* loss_scale;     // device scalar (amp) or null => 1
-  __nv_bfloat16* da;           // [B,512] grad wrt a (before the ReLU mask)
+  void* da;                    // [B,512] grad wrt a (before the ReLU mask), same type as a
   float* dw;                   // [10,512] += dlogits^T a
   float* db;                   // [10]     += sum dlogits
   const float* dlogits;        // optional [B,10]: externally supplied d(loss)/d(logits) (autograd path)
@@ -119,8 +120,30 @@ struct HeadArgs {
 };
 int head_partial_cols();
 void launch_head(const HeadArgs& args, cudaStream_t s);
+void launch_head_f16(const HeadArgs& args, cudaStream_t s);
 
 // [c_out][taps][c_in] -> [c_in][taps][c_out] (bf16): K-major weights for the data gradient
 void launch_transpose_taps(const __nv_bfloat16* w, __nv_bfloat16* wt, int c_out, int taps, int c_in, cudaStream_t s);
+
+
+// ---- fp16-activation overloads (O1-fp16: Apex O1's precision in the reference); same semantics, same launch shapes.
+// Defined by csrc/nn/toynet_elementwise_f16.cu, which rebuilds toynet_elementwise.cu with act_t = __half.
+int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/, const float* bias,
+                     __half* y, float* stat_partials /*[rows][2][64] or null*/, double* stat_accum,
+                     int batch, cudaStream_t s);
+void launch_conv0_wgrad(const void* x, int x_is_u8, const __half* dy, float* dw, float* db, float* partials,
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s);
+void launch_bn_relu_pool(const __half* y, const float* scale, const float* shift, __half* out, int n,
+                         int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
+                         const BnFusedFwd& fused, cudaStream_t s);
+int launch_bn_bwd_reduce(const __half* y, const __half* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, float* partials, double* accum /*[2][C] or null*/,
+                         int n, int h, int w, int c, int pool, int g_flatten_chw, cudaStream_t s);
+void launch_chw_to_hwc(const __half* in, __half* out, int n, int c, int p, cudaStream_t s);
+void launch_bn_bwd_apply(const __half* y, const __half* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* coef, __half* dy,
+                         float* dbias /*[C] atomics or null*/, const BnFusedBwd& fused, int n, int h, int w, int c,
+                         int pool, int g_flatten_chw, cudaStream_t s);
+void launch_transpose_taps(const __half* w, __half* wt, int c_out, int taps, int c_in, cudaStream_t s);
 
 }  // namespace ddpt

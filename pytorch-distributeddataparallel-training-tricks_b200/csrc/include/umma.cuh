@@ -198,6 +198,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, b
          | ((m >> 4) << 24);            // m_dim
 }
 
+// kind::f16 takes bf16 or fp16 operands: format 1 = BF16, 0 = F16.  XOR-ing this mask into a bf16 descriptor turns both
+// operand formats into F16 (the "O1-fp16" path: same kernels, same layouts, different 16-bit format).
+constexpr uint32_t kIdescBf16ToF16 = (1u << 7) | (1u << 10);
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by one thread.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {

@@ -47,6 +47,7 @@ struct KernelArgs {
   double* stat_accum;
   int relu, out_fp32, a_rows_bytes;
   long long slab_stride;        // split-K: > 0 = every split stores its own slab (no atomics)
+  int fp16;                     // operands and 16-bit outputs are fp16 instead of bf16
 };
 
 template <int BN, bool B_MN>
@@ -55,7 +56,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const KernelArgs args) {
   constexpr int kStages = stages_for<BN>();
   constexpr int kBStageBytes = BN * kBlockK * 2;
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+  const uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -228,10 +229,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
-            pk.x = pack_bf16x2(f[j], f[j + 1]);
-            pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-            pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-            pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+            if (args.fp16) {
+              pk.x = pack_f16x2(f[j], f[j + 1]); pk.y = pack_f16x2(f[j + 2], f[j + 3]);
+              pk.z = pack_f16x2(f[j + 4], f[j + 5]); pk.w = pack_f16x2(f[j + 6], f[j + 7]);
+            } else {
+              pk.x = pack_bf16x2(f[j], f[j + 1]); pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              pk.z = pack_bf16x2(f[j + 4], f[j + 5]); pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+            }
             *reinterpret_cast<uint4*>(o + j) = pk;
           }
         }
@@ -266,6 +270,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
   a.slab_stride = p.split_k > 1 ? p.split_slab_stride : 0;
+  a.fp16 = p.fp16;
 
   if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)
     throw std::runtime_error("conv_gemm: unsupported shape (C % 64, N % BLOCK_N, brick <= 128 rows)");
@@ -331,7 +336,7 @@ constexpr int kFinishThreads = 256;
 
 __global__ void __launch_bounds__(kFinishThreads)
 splitk_finish_kernel(const float* __restrict__ slabs, int splits, long long slab_stride, int rows, int cols,
-                     __nv_bfloat16* __restrict__ out, float* __restrict__ stat_partials) {
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ stat_partials, int fp16) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float s_part[];                       // [rows_per_blk][2][cols] ordered block fold
@@ -350,7 +355,8 @@ splitk_finish_kernel(const float* __restrict__ slabs, int splits, long long slab
       b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
     }
     uint4 pk;
-    pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+    if (fp16) { pk.x = pack_f16x2(a.x, a.y); pk.y = pack_f16x2(a.z, a.w); pk.z = pack_f16x2(b.x, b.y); pk.w = pack_f16x2(b.z, b.w); }
+    else { pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w); }
     *reinterpret_cast<uint4*>(out + (long long)r * cols + v * 8) = pk;
     const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -372,14 +378,14 @@ splitk_finish_kernel(const float* __restrict__ slabs, int splits, long long slab
 int splitk_finish_max_rows() { return sm_count() * 2; }
 
 int launch_splitk_finish(const float* slabs, int splits, long long slab_stride, int rows, int cols,
-                         __nv_bfloat16* out, float* stat_partials, cudaStream_t stream) {
+                         __nv_bfloat16* out, float* stat_partials, int fp16, cudaStream_t stream) {
   if (cols % 8 != 0 || kFinishThreads % (cols / 8) != 0) throw std::runtime_error("splitk_finish: cols must be 8 x a divisor of 256");
   const int rows_per_blk = kFinishThreads / (cols / 8);
   int grid = (rows + rows_per_blk - 1) / rows_per_blk;
   if (grid > splitk_finish_max_rows()) grid = splitk_finish_max_rows();
   const size_t smem = (size_t)rows_per_blk * 2 * cols * sizeof(float);
   launch_pdl(splitk_finish_kernel, dim3(grid), dim3(kFinishThreads), smem, stream, slabs, splits, slab_stride, rows, cols, out,
-             stat_partials);
+             stat_partials, fp16);
   DDPT_CUDA_CHECK(cudaGetLastError());
   return grid;
 }

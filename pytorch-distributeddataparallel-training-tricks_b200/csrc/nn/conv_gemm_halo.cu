@@ -49,6 +49,7 @@ struct HaloArgs {
   float* stat_partials;
   double* stat_accum;
   int relu, out_fp32;
+  int fp16;                         // operands and 16-bit outputs are fp16 instead of bf16
 };
 
 // NI = 2 (resident weights, BN <= 128): TWO MMA-issuing warps.  A 128 x 64 x 16 MMA is 32 tensor cycles, less than one
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kThreads + 32 * (NI - 1), 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const HaloArgs args, const int num_m_tiles, const int num_n_tiles) {
   constexpr int kBStageBytes = BN * kBlockK * 2;
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+  const uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, false, B_MN) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
   constexpr uint32_t kTmemCols = 2 * BN * NI;
   static_assert(NI == 1 || (NI == 2 && B_RES && BN <= 128), "two issuers: resident weights, 2 x 2 x BN TMEM columns");
   static_assert(KC == 0 || (B_RES && NI == 1), "unrolled issuer: resident weights, single issuer");
@@ -332,10 +333,13 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 pk;
-              pk.x = pack_bf16x2(f[j], f[j + 1]);
-              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              if (args.fp16) {
+                pk.x = pack_f16x2(f[j], f[j + 1]); pk.y = pack_f16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_f16x2(f[j + 4], f[j + 5]); pk.w = pack_f16x2(f[j + 6], f[j + 7]);
+              } else {
+                pk.x = pack_bf16x2(f[j], f[j + 1]); pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_bf16x2(f[j + 4], f[j + 5]); pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              }
               *reinterpret_cast<uint4*>(o + j) = pk;
             }
           }
@@ -398,7 +402,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   const int view_rows = (16 + (p.taps_h - 1) * p.box_n) * 8;
   a.a_slot_bytes = round_up((view_rows > halo_rows ? view_rows : halo_rows) * 128, 1024);
   a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias; a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum;
-  a.relu = p.relu; a.out_fp32 = p.out_fp32;
+  a.relu = p.relu; a.out_fp32 = p.out_fp32; a.fp16 = p.fp16;
 
   const int total_kb = p.taps_h * p.taps_w * a.k_chunks;
   const long long b_res_bytes = (long long)total_kb * kBStageBytes;

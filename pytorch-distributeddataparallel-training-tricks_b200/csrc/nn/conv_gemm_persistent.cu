@@ -61,6 +61,7 @@ struct KernelArgs {
   int pair_interleave;          // CTA pair: the two row tiles of a unit are the same pixel brick of adjacent image groups
   const int* schedule;          // optional host-planned work lists: schedule[cta * sched_len + k] = k-th unit of CTA (pair)
   int sched_len;                // `cta`, -1 terminated; null: round robin (unit = cta + k * #ctas)
+  int fp16;                     // operands and 16-bit outputs are fp16 instead of bf16
 };
 
 // k-th work unit of this CTA (pair), or -1 when it has none left.  Data-gradient tiles cost between 1 and taps_h x taps_w
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const KernelArgs args, const int num_m_tiles, const int num_n_tiles) {
   constexpr int kBStageBytes = (BN / MC) * kBlockK * 2;     // one K block of B (this CTA's share of the columns)
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM * MC, BN, false, B_MN);
+  const uint32_t kIdesc = make_idesc_bf16(kBlockM * MC, BN, false, B_MN) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
   constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator stages
 
   // CTA pair: streamed weights; an MN-major weight tile is loaded in 64-column boxes, so a pair needs BN >= 128 there.
@@ -409,10 +410,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 pk;
-              pk.x = pack_bf16x2(f[j], f[j + 1]);
-              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              if (args.fp16) {
+                pk.x = pack_f16x2(f[j], f[j + 1]); pk.y = pack_f16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_f16x2(f[j + 4], f[j + 5]); pk.w = pack_f16x2(f[j + 6], f[j + 7]);
+              } else {
+                pk.x = pack_bf16x2(f[j], f[j + 1]); pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                pk.z = pack_bf16x2(f[j + 4], f[j + 5]); pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              }
               *reinterpret_cast<uint4*>(o + j) = pk;
             }
           }
@@ -540,7 +544,7 @@ int launch_persistent_impl(const ConvGemmProblem& p, cudaStream_t stream) {
   a.n_total = p.n_total; a.ld_out = p.ld_out; a.out = p.out; a.bias = p.bias;
   a.stat_partials = p.stat_partials; a.stat_accum = p.stat_accum; a.relu = p.relu; a.out_fp32 = p.out_fp32;
   a.a_rows_bytes = p.box_w * p.box_h * p.box_n * kBlockK * 2;
-  a.a_w = p.a_w; a.a_h = p.a_h;
+  a.a_w = p.a_w; a.a_h = p.a_h; a.fp16 = p.fp16;
   a.pair_interleave = (MC == 2 && tiles_n % 2 == 0 && p.taps_h * p.taps_w > 1) ? 1 : 0;
 
   if (p.a_c % kBlockK != 0 || p.n_total % BN != 0 || p.box_w * p.box_h * p.box_n > kBlockM)

@@ -16,26 +16,60 @@
 #include <cstdlib>
 #include <stdexcept>
 
+// ---- activation precision -------------------------------------------------------------------------------------------
+// This translation unit is compiled twice: as is for bf16 activations (the default "O1"), and through
+// toynet_elementwise_f16.cu (which defines DDPT_ACT_F16 and includes this file) for fp16 activations -- Apex O1's actual
+// precision in the reference (utils/train.py:58).  Every kernel is written against act_t / act2_t and the six helpers
+// below; the public launchers are C++ overloads on the activation pointer type, so both builds link into one library.
+#ifdef DDPT_ACT_F16
+#include <cuda_fp16.h>
+#endif
+
 namespace ddpt {
 namespace {
+
+#ifdef DDPT_ACT_F16
+using act_t = __half;
+using act2_t = __half2;
+__device__ __forceinline__ float2 act2_to_float2(act2_t v) { return __half22float2(v); }
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ act_t to_act(float f) { return __float2half_rn(f); }
+__device__ __forceinline__ act_t to_act_rd(float f) { return __float2half_rd(f); }
+__device__ __forceinline__ float from_act(act_t v) { return __half2float(v); }
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __half2float(__ushort_as_half((unsigned short)(x & 0xffffu))); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __half2float(__ushort_as_half((unsigned short)(x >> 16))); }
+#else
+using act_t = __nv_bfloat16;
+using act2_t = __nv_bfloat162;
+__device__ __forceinline__ float2 act2_to_float2(act2_t v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) { return pack_bf16x2(lo, hi); }
+__device__ __forceinline__ act_t to_act(float f) { return __float2bfloat16(f); }
+__device__ __forceinline__ act_t to_act_rd(float f) { return __float2bfloat16_rd(f); }
+__device__ __forceinline__ float from_act(act_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }          // low / high element of a packed pair
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+#endif
 
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const act2_t* p = reinterpret_cast<const act2_t*>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p[i]);
+    float2 t = act2_to_float2(p[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 v;
-  v.x = pack_bf16x2(f[0], f[1]);
-  v.y = pack_bf16x2(f[2], f[3]);
-  v.z = pack_bf16x2(f[4], f[5]);
-  v.w = pack_bf16x2(f[6], f[7]);
+  v.x = pack_act2(f[0], f[1]);
+  v.y = pack_act2(f[2], f[3]);
+  v.z = pack_act2(f[4], f[5]);
+  v.w = pack_act2(f[6], f[7]);
   return v;
 }
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -91,7 +125,7 @@ __device__ __forceinline__ void load_image(const void* x, int x_is_u8, int img, 
 
 __global__ void __launch_bounds__(kThreads)
 conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restrict__ weight,
-                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ partials,
+                 const float* __restrict__ bias, act_t* __restrict__ y, float* __restrict__ partials,
                  double* __restrict__ accum, int batch) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
@@ -154,7 +188,7 @@ conv0_fwd_kernel(const void* __restrict__ x, int x_is_u8, const float* __restric
 }
 
 __global__ void __launch_bounds__(kThreads)
-conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16* __restrict__ dy,
+conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const act_t* __restrict__ dy,
                    float* __restrict__ dw, float* __restrict__ db, float* __restrict__ partials, int batch,
                    const Conv0BnFuse bn) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
@@ -195,7 +229,7 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
         const int p = p0 + u * kStep;
         if (p < kPix0) {
           const size_t off = ((size_t)img * kPix0 + p) * kC0 + cg * 8;
-          if (fused) { raw[u] = ldg16(bn.g + off); rawy[u] = ldg16(bn.y + off); }
+          if (fused) { raw[u] = ldg16(static_cast<const act_t*>(bn.g) + off); rawy[u] = ldg16(static_cast<const act_t*>(bn.y) + off); }
           else raw[u] = ldg16(dy + off);
         }
       }
@@ -212,7 +246,7 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const __nv_bfloat16*
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float dz = fmaf(yv[j], f_sc[j], f_sh[j]) > 0.f ? g[j] : 0.f;
-            g[j] = __bfloat162float(__float2bfloat16(fmaf(f_c1[j], dz, fmaf(-f_k1[j], yv[j], f_k0[j]))));
+            g[j] = from_act(to_act(fmaf(f_c1[j], dz, fmaf(-f_k1[j], yv[j], f_k0[j]))));
           }
         }
         float in[9];
@@ -391,8 +425,8 @@ __device__ __forceinline__ void load8s(const float* p, float (&f)[8]) {
 // loads of U pixels are issued before any arithmetic (these passes are latency-, not bandwidth-limited otherwise).
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
-bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
+bn_relu_pool_kernel(const act_t* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, act_t* __restrict__ out, int n, int h, int w, int c,
                     uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale, const BnFusedFwd st) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
@@ -422,7 +456,7 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
         raw[u][0] = ldg16(y + (size_t)pix * c + v * 8);
       } else {
         const unsigned pw = pix % ow, ph = (pix / ow) % oh, img = pix / ((unsigned)ow * oh);
-        const __nv_bfloat16* base = y + (((size_t)img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
+        const act_t* base = y + (((size_t)img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
 #pragma unroll
         for (int q = 0; q < 4; ++q) raw[u][q] = ldg16(base + ((q >> 1) * w + (q & 1)) * c);
       }
@@ -464,12 +498,12 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
 
 // Pooled + flattened in (c, ph, pw) order for the first Linear: one block per image, smem transpose.
 __global__ void __launch_bounds__(kThreads)
-bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int h, int w, int c,
+bn_relu_pool_flatten_kernel(const act_t* __restrict__ y, const float* __restrict__ scale,
+                            const float* __restrict__ shift, act_t* __restrict__ out, int h, int w, int c,
                             uint8_t* __restrict__ q_out, uint8_t* __restrict__ q_scale, const BnFusedFwd st) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
-  extern __shared__ __nv_bfloat16 s_t[];                  // [c][ppix + 2] (padded)
+  extern __shared__ act_t s_t[];                  // [c][ppix + 2] (padded)
   __shared__ float s_sc[512], s_sh[512];
   const bool fused = st.accum != nullptr;
   if (fused) fused_fwd_coeffs(st, c, s_sc, s_sh);
@@ -483,7 +517,7 @@ bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __
     else { load8f(scale + v * 8, sc); load8f(shift + v * 8, sh); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) r[k] = 0.f;
-    const __nv_bfloat16* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
+    const act_t* base = y + ((img * h + 2 * ph) * w + 2 * pw) * c + v * 8;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float f[8];
@@ -492,10 +526,10 @@ bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __
       for (int k = 0; k < 8; ++k) r[k] = fmaxf(r[k], fmaf(f[k], sc[k], sh[k]));
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s_t[(v * 8 + k) * ld + pp] = __float2bfloat16(r[k]);
+    for (int k = 0; k < 8; ++k) s_t[(v * 8 + k) * ld + pp] = to_act(r[k]);
   }
   __syncthreads();
-  __nv_bfloat16* dst = out + img * (long long)c * ppix;
+  act_t* dst = out + img * (long long)c * ppix;
   for (int i = threadIdx.x; i < c * ppix; i += kThreads) dst[i] = s_t[(i / ppix) * ld + (i % ppix)];
   if (q_out != nullptr) {
     // MXFP8 copy of the flattened row: blocks of 32 consecutive outputs (the K dimension of the first Linear)
@@ -506,7 +540,7 @@ bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int i = b * 32 + j;
-        vals[j] = __bfloat162float(s_t[(i / ppix) * ld + (i % ppix)]);
+        vals[j] = from_act(s_t[(i / ppix) * ld + (i % ppix)]);
         amax = fmaxf(amax, vals[j]);
       }
       const int e = mx_exponent(amax);
@@ -528,7 +562,7 @@ bn_relu_pool_flatten_kernel(const __nv_bfloat16* __restrict__ y, const float* __
 // ================================================================================================
 // dz for one 8-channel vector of one (pooled) output position; also returns xhat at the routed position(s).
 struct BwdCtx {
-  const __nv_bfloat16* y; const __nv_bfloat16* g;
+  const act_t* y; const act_t* g;
   const float* scale; const float* shift; const float* mean; const float* invstd;
   int n, h, w, c, flatten;
 };
@@ -538,9 +572,9 @@ __device__ __forceinline__ void load_g(const BwdCtx& k, long long img, int ph, i
   if (!k.flatten) {
     unpack8(ldg16(k.g + ((img * oh + ph) * ow + pw) * k.c + v * 8), g);
   } else {
-    const __nv_bfloat16* base = k.g + img * (long long)k.c * oh * ow + (long long)(v * 8) * oh * ow + ph * ow + pw;
+    const act_t* base = k.g + img * (long long)k.c * oh * ow + (long long)(v * 8) * oh * ow + ph * ow + pw;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = __bfloat162float(base[(long long)j * oh * ow]);
+    for (int j = 0; j < 8; ++j) g[j] = from_act(base[(long long)j * oh * ow]);
   }
 }
 
@@ -562,7 +596,7 @@ __device__ __forceinline__ PoolConsts pool_consts(const float (&sc)[8], const fl
     for (int hlf = 0; hlf < 2; ++hlf) {
       const float a = sc[2 * i + hlf], b = sh[2 * i + hlf];
       const float t = a == 0.f ? (b > 0.f ? -INFINITY : INFINITY) : -b / fabsf(a);
-      const __nv_bfloat16 tb = __float2bfloat16_rd(t);
+      const act_t tb = to_act_rd(t);
       th |= (uint32_t)(*reinterpret_cast<const unsigned short*>(&tb)) << (16 * hlf);
       sg |= (a < 0.f ? 0x8000u : 0u) << (16 * hlf);
     }
@@ -571,13 +605,11 @@ __device__ __forceinline__ PoolConsts pool_consts(const float (&sc)[8], const fl
   }
   return pc;
 }
-__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t x) { return *reinterpret_cast<__nv_bfloat162*>(&x); }
+__device__ __forceinline__ act2_t as_bf162(uint32_t x) { return *reinterpret_cast<act2_t*>(&x); }
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hmax2(as_bf162(a), as_bf162(b));
+  const act2_t r = __hmax2(as_bf162(a), as_bf162(b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
-__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
 __device__ __forceinline__ uint32_t comp(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 // pooled gradient of one output position as four bf16x2 words (NHWC rows, or the flattened [c][oh][ow] layout
@@ -631,7 +663,7 @@ bn_bwd_reduce_kernel(BwdCtx k, float* __restrict__ partials, double* __restrict_
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (pix + u * stride32 < total32) {
-          const __nv_bfloat16* base = k.y + (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
+          const act_t* base = k.y + (((size_t)img[u] * k.h + 2 * ph[u]) * k.w + 2 * pw[u]) * k.c + v * 8;
 #pragma unroll
           for (int q = 0; q < 4; ++q) yq[u][q] = ldg16(base + ((q >> 1) * k.w + (q & 1)) * k.c);
           gq[u] = load_g_packed(k, img[u], ph[u], pw[u], oh, ow, v);
@@ -775,7 +807,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int
 // one global atomic per channel per CTA); the reference's numerical value is rounding noise of order 1e-7.
 template <bool POOL, bool HAS_DB>
 __global__ void __launch_bounds__(kThreads, 2)
-bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
+bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, act_t* __restrict__ dy,
                     float* __restrict__ dbias, const BnFusedBwd fb) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
@@ -881,7 +913,7 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
             const float lo = fmaf(c1[2 * i], bf_lo(dz[q][i]), fmaf(-k1[2 * i], bf_lo(yw), k0[2 * i]));
             const float hi = fmaf(c1[2 * i + 1], bf_hi(dz[q][i]), fmaf(-k1[2 * i + 1], bf_hi(yw), k0[2 * i + 1]));
             if (HAS_DB) { db[2 * i] += lo; db[2 * i + 1] += hi; }
-            o[i] = pack_bf16x2(lo, hi);
+            o[i] = pack_act2(lo, hi);
           }
           *reinterpret_cast<uint4*>(dy + base_off[u] + ((q >> 1) * k.w + (q & 1)) * k.c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -957,27 +989,27 @@ bn_bwd_apply_kernel(BwdCtx k, const float* __restrict__ coef, __nv_bfloat16* __r
 // passes): 49.6 + 63.4 us at 1.7 TB/s for conv.10, long-scoreboard bound (profiles/ncu_bnbwd_v9.txt).
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads)
-chw_to_hwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c, int p) {
+chw_to_hwc_kernel(const act_t* __restrict__ in, act_t* __restrict__ out, int n, int c, int p) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
-  extern __shared__ __nv_bfloat16 s_tile[];                // [c][p + 2]
+  extern __shared__ act_t s_tile[];                // [c][p + 2]
   const int pitch = p + 2;
   const int vec_per_img = c * p / 8;
   for (int img = blockIdx.x; img < n; img += gridDim.x) {
-    const __nv_bfloat16* src = in + (size_t)img * c * p;
+    const act_t* src = in + (size_t)img * c * p;
     for (int i = threadIdx.x; i < vec_per_img; i += kThreads) {
       const uint4 v = ldg16(src + (size_t)i * 8);
-      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+      const act_t* e = reinterpret_cast<const act_t*>(&v);
       const int flat = i * 8, ch = flat / p, pos = flat - ch * p;   // p % 8 == 0: one vector stays in one channel
 #pragma unroll
       for (int j = 0; j < 8; ++j) s_tile[ch * pitch + pos + j] = e[j];
     }
     __syncthreads();
-    __nv_bfloat16* dst = out + (size_t)img * c * p;
+    act_t* dst = out + (size_t)img * c * p;
     const int cv = c / 8;
     for (int i = threadIdx.x; i < vec_per_img; i += kThreads) {
       const int pos = i / cv, v = i - pos * cv;
-      __nv_bfloat16 e[8];
+      act_t e[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) e[j] = s_tile[(v * 8 + j) * pitch + pos];
       *reinterpret_cast<uint4*>(dst + (size_t)pos * c + v * 8) = *reinterpret_cast<const uint4*>(e);
@@ -1021,8 +1053,8 @@ head_kernel(HeadArgs a) {
     // lane owns features {64*j + 2*lane + e : j < 8, e < 2}: 4-byte coalesced loads, conflict-light smem
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(a.a + (size_t)row * kFeat + 64 * j + 2 * lane);
-      const float2 f = __bfloat1622float2(v);
+      const act2_t v = *reinterpret_cast<const act2_t*>(static_cast<const act_t*>(a.a) + (size_t)row * kFeat + 64 * j + 2 * lane);
+      const float2 f = act2_to_float2(v);
       x[2 * j] = f.x;
       x[2 * j + 1] = f.y;
     }
@@ -1071,7 +1103,7 @@ head_kernel(HeadArgs a) {
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint32_t*>(a.da + (size_t)row * kFeat + 64 * j + 2 * lane) = pack_bf16x2(dx[2 * j], dx[2 * j + 1]);
+        *reinterpret_cast<uint32_t*>(static_cast<act_t*>(a.da) + (size_t)row * kFeat + 64 * j + 2 * lane) = pack_act2(dx[2 * j], dx[2 * j + 1]);
     }
     }  // active
     if (train) {
@@ -1124,7 +1156,7 @@ head_kernel(HeadArgs a) {
 // w [c_out][taps][c_in] (the K-major forward weight) -> wt [c_in][taps][c_out]: the K-major operand of the data
 // gradient (reduction over c_out), which lets the 64-column data gradient run as a CTA pair.  144 KiB for conv.3.
 __global__ void __launch_bounds__(kThreads)
-transpose_taps_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int c_out, int taps, int c_in) {
+transpose_taps_kernel(const act_t* __restrict__ w, act_t* __restrict__ wt, int c_out, int taps, int c_in) {
   pdl_wait();
   pdl_trigger();
   const int total = c_out * taps * c_in;
@@ -1136,7 +1168,7 @@ transpose_taps_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __rest
 
 }  // namespace
 
-void launch_transpose_taps(const __nv_bfloat16* w, __nv_bfloat16* wt, int c_out, int taps, int c_in, cudaStream_t s) {
+void launch_transpose_taps(const act_t* w, act_t* wt, int c_out, int taps, int c_in, cudaStream_t s) {
   const int total = c_out * taps * c_in;
   int grid = (total + kThreads - 1) / kThreads;
   if (grid > 4 * sm_count()) grid = 4 * sm_count();
@@ -1145,9 +1177,11 @@ void launch_transpose_taps(const __nv_bfloat16* w, __nv_bfloat16* wt, int c_out,
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
+#ifndef DDPT_ACT_F16
 int conv0_partial_rows() { return sm_count() * 2; }
 
-int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const float* bias, __nv_bfloat16* y,
+#endif
+int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const float* bias, act_t* y,
                      float* stat_partials, double* stat_accum, int batch, cudaStream_t s) {
   const int grid = batch < conv0_partial_rows() ? batch : conv0_partial_rows();
   launch_pdl(conv0_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, weight, bias, y, stat_partials, stat_accum, batch);
@@ -1155,9 +1189,11 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight, const floa
   return grid;
 }
 
+#ifndef DDPT_ACT_F16
 int conv0_wgrad_partial_rows() { return sm_count() * 2; }
 
-void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
+#endif
+void launch_conv0_wgrad(const void* x, int x_is_u8, const act_t* dy, float* dw, float* db, float* partials,
                         int batch, const Conv0BnFuse& bn, cudaStream_t s) {
   // the fused variant holds 40 more per-thread constants (177 registers): one resident CTA per SM, so one CTA per SM
   const int per_sm = bn.y != nullptr ? 1 : 2;
@@ -1171,6 +1207,7 @@ void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, flo
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
+#ifndef DDPT_ACT_F16
 void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                         const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
                         float* running_var, long long* nbt, cudaStream_t s) {
@@ -1187,12 +1224,13 @@ void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* r
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
+#endif
 static void check_channels(int c) {
   if (c % 8 != 0 || kThreads % (c / 8) != 0 || c > 2048)
     throw std::runtime_error("toynet elementwise kernels need C % 8 == 0 and (C/8) dividing 256");
 }
 
-void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* out, int n,
+void launch_bn_relu_pool(const act_t* y, const float* scale, const float* shift, act_t* out, int n,
                          int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
                          const BnFusedFwd& fused, cudaStream_t s) {
   check_channels(c);
@@ -1201,7 +1239,7 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
   if (flatten_chw) {
     if (!pool) throw std::runtime_error("flatten_chw is only implemented together with the pool");
     const int ppix = (h / 2) * (w / 2);
-    const size_t smem = (size_t)c * (ppix + 2) * sizeof(__nv_bfloat16);
+    const size_t smem = (size_t)c * (ppix + 2) * sizeof(act_t);
     launch_pdl(bn_relu_pool_flatten_kernel, dim3(n), dim3(kThreads), smem, s, y, scale, shift, out, h, w, c, q_out, q_scale, fused);
   } else {
     const long long pixels = (long long)n * (pool ? (h / 2) * (w / 2) : h * w);
@@ -1214,9 +1252,11 @@ void launch_bn_relu_pool(const __nv_bfloat16* y, const float* scale, const float
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
+#ifndef DDPT_ACT_F16
 int bn_bwd_partial_rows() { return sm_count() * 4; }
 
-int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
+#endif
+int launch_bn_bwd_reduce(const act_t* y, const act_t* g, const float* scale, const float* shift,
                          const float* mean, const float* invstd, float* partials, double* accum, int n, int h, int w,
                          int c, int pool, int g_flatten_chw, cudaStream_t s) {
   check_channels(c);
@@ -1234,6 +1274,7 @@ int launch_bn_bwd_reduce(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   return grid;
 }
 
+#ifndef DDPT_ACT_F16
 void launch_bn_bwd_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                             const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
                             int accumulate, cudaStream_t s) {
@@ -1242,8 +1283,9 @@ void launch_bn_bwd_finalize(const float* partials, int num_partials, int channel
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const float* scale, const float* shift,
-                         const float* mean, const float* invstd, const float* coef, __nv_bfloat16* dy, float* dbias,
+#endif
+void launch_bn_bwd_apply(const act_t* y, const act_t* g, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* coef, act_t* dy, float* dbias,
                          const BnFusedBwd& fused, int n, int h, int w, int c, int pool, int g_flatten_chw,
                          cudaStream_t s) {
   check_channels(c);
@@ -1273,9 +1315,15 @@ void launch_bn_bwd_apply(const __nv_bfloat16* y, const __nv_bfloat16* g, const f
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
+#ifndef DDPT_ACT_F16
 int head_partial_cols() { return kHeadPartialCols; }
 
+#endif
+#ifdef DDPT_ACT_F16
+void launch_head_f16(const HeadArgs& args, cudaStream_t s) {
+#else
 void launch_head(const HeadArgs& args, cudaStream_t s) {
+#endif
   int grid = (args.batch + kHeadRows - 1) / kHeadRows;
   const int cap = sm_count();
   if (grid > cap) grid = cap;
@@ -1294,9 +1342,9 @@ void launch_head(const HeadArgs& args, cudaStream_t s) {
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_chw_to_hwc(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int c, int p, cudaStream_t s) {
+void launch_chw_to_hwc(const act_t* in, act_t* out, int n, int c, int p, cudaStream_t s) {
   if (p % 8 != 0 || c % 8 != 0) throw std::runtime_error("chw_to_hwc: C and H*W must be multiples of 8");
-  const size_t smem = (size_t)c * (p + 2) * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)c * (p + 2) * sizeof(act_t);
   if (smem > 48 * 1024) throw std::runtime_error("chw_to_hwc: one image does not fit 48 KiB of shared memory");
   const int grid = n < 4 * sm_count() ? n : 4 * sm_count();
   launch_pdl(chw_to_hwc_kernel, dim3(grid), dim3(kThreads), smem, s, in, out, n, c, p);

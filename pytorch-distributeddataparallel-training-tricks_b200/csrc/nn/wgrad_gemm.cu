@@ -36,6 +36,7 @@ struct WgradArgs {
   int stages, slot_bytes;            // pipeline depth and bytes of one 64-channel column block
   float* dw;
   int use_red;
+  int fp16;                          // operands are fp16 instead of bf16
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -46,7 +47,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradArgs args) {
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, true, true);
+  const uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, true, true) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
   constexpr int kABlocks = kBlockM / 64, kBBlocks = BN / 64;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,6 +176,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 template <int BN>
 void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   WgradArgs a{};
+  a.fp16 = p.fp16;
   a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
   a.brick_rows = p.box_w * p.box_h * p.box_n;
   a.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;

@@ -49,6 +49,7 @@ struct MtArgs {
   float* slab;                 // optional [gridDim.z][M * taps * C] partial slabs written with plain stores
   long long slab_elems;
   int plain;                   // no slab, single split, beta = 0: plain stores straight into dw
+  int fp16;                    // operands are fp16 instead of bf16
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -59,7 +60,7 @@ template <int BN, int TMEM_COLS>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x0,
                       const __grid_constant__ CUtensorMap tmap_x1, const MtArgs args) {
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, true, true);
+  const uint32_t kIdesc = make_idesc_bf16(kBlockM, BN, true, true) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
   constexpr int kABlocks = kBlockM / 64, kBBlocks = BN / 64;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,7 +153,7 @@ wgrad_multitap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
           // brick starts box_n * xw rows after tap dr-1's, which is exactly the descriptor's leading-dimension
           // stride.  N = taps * 64 (<= 256) amortises the A-operand fetch and the issue slot over all taps; a
           // 128-channel tile is two such MMAs (one per 64-channel block), accumulators laid out [block][tap][64].
-          const uint32_t idesc_wide = make_idesc_bf16(kBlockM, 64 * box_taps, true, true);
+          const uint32_t idesc_wide = make_idesc_bf16(kBlockM, 64 * box_taps, true, true) ^ (args.fp16 ? kIdescBf16ToF16 : 0u);
           const uint32_t tap_pitch = args.box_n * xw * 128;
           // K step k covers the 8-pixel groups 2k, 2k+1 of the brick: (row, column group) advance with counters --
           // a runtime division per MMA on the issuing lane costs more than the MMA itself
@@ -271,6 +272,7 @@ reduce_slabs_kernel(const float4* __restrict__ slab, float4* __restrict__ out, l
 template <int BN>
 void launch_impl(const WgradProblem& p, cudaStream_t stream) {
   MtArgs a{};
+  a.fp16 = p.fp16;
   a.box_w = p.box_w; a.box_h = p.box_h; a.box_n = p.box_n;
   a.brick_rows = p.box_w * p.box_h * p.box_n;
   a.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;

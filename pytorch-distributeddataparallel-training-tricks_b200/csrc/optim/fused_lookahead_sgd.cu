@@ -32,10 +32,11 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 
-__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* dst, float4 v) {
+// 16-bit weight shadow: bf16 (O1) or fp16 (O1-fp16)
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* dst, float4 v, int fp16 = 0) {
   uint2 packed;
-  packed.x = pack_bf16x2(v.x, v.y);
-  packed.y = pack_bf16x2(v.z, v.w);
+  if (fp16) { packed.x = pack_f16x2(v.x, v.y); packed.y = pack_f16x2(v.z, v.w); }
+  else { packed.x = pack_bf16x2(v.x, v.y); packed.y = pack_bf16x2(v.z, v.w); }
   *reinterpret_cast<uint2*>(dst) = packed;
 }
 
@@ -101,7 +102,7 @@ fused_lookahead_sgd_kernel(FusedSgdArgs a) {
       p4[i] = p[u];
       m4[i] = m[u];
       if (sync) s4[i] = s[u];
-      if (a.shadow != nullptr) st_bf16x4(a.shadow + 4 * i, p[u]);
+      if (a.shadow != nullptr) st_bf16x4(a.shadow + 4 * i, p[u], a.shadow_fp16);
       if (z4 != nullptr) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -125,11 +126,11 @@ fused_lookahead_sgd_kernel(FusedSgdArgs a) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-cast_bf16_kernel(const float4* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec) {
+cast_bf16_kernel(const float4* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec, int fp16) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads)
-    st_bf16x4(dst + 4 * i, src[i]);
+    st_bf16x4(dst + 4 * i, src[i], fp16);
 }
 
 }  // namespace
@@ -144,13 +145,13 @@ void launch_fused_lookahead_sgd(const FusedSgdArgs& args, cudaStream_t stream) {
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long numel, cudaStream_t stream) {
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long numel, cudaStream_t stream, int fp16) {
   const long long nvec = numel >> 2;
   if (nvec <= 0) return;
   long long want = (nvec + kThreads - 1) / kThreads;
   const int cap = sm_count() * 8;
   launch_pdl(cast_bf16_kernel, dim3((int)(want < cap ? want : cap)), dim3(kThreads), 0, stream, 
-      reinterpret_cast<const float4*>(src), dst, nvec);
+      reinterpret_cast<const float4*>(src), dst, nvec, fp16);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -76,7 +76,7 @@ def deterministic() -> bool:
 def attach_fused_model(model: torch.nn.Module, compute: Optional[str]) -> bool:
     """Give ``model`` its fused sm_100a forward/backward if one exists for its type."""
     from ..models import Toy_Net
-    if isinstance(model, Toy_Net) and compute in ("bf16", "fp8"):
+    if isinstance(model, Toy_Net) and compute in ("bf16", "fp16", "fp8"):
         from . import toynet_fused
         return toynet_fused.attach(model, compute)
     return False

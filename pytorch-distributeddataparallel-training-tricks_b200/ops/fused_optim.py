@@ -23,7 +23,7 @@ STATE_STEP, STATE_LA_COUNTER, STATE_SLOW_READY, STATE_K, STATE_TICKET, STATE_SKI
 
 class FusedState:
     def __init__(self, sgd, params: List[torch.nn.Parameter], scaler, arena: Optional[FlatArena] = None,
-                 bucket_cap_mb: float = 25.0):
+                 bucket_cap_mb: float = 25.0, shadow_dtype: torch.dtype = torch.bfloat16):
         self.ext = require_native()
         self.params = params
         self.scaler = scaler
@@ -32,7 +32,8 @@ class FusedState:
         n = self.arena.numel
         self.momentum = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.slow: Optional[torch.Tensor] = None
-        self.shadow = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+        self.shadow_dtype = shadow_dtype       # bf16 (O1) or fp16 (O1-fp16): the tensor-core operand format
+        self.shadow = torch.empty(n, dtype=shadow_dtype, device=self.device)
         self.hyper = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.state = torch.zeros(8, dtype=torch.int32, device=self.device)
         self._hyper_host = None
@@ -49,7 +50,7 @@ class FusedState:
             n = arena.numel
             self.momentum = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.slow = None if self.slow is None else torch.zeros(n, dtype=torch.float32, device=self.device)
-            self.shadow = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            self.shadow = torch.empty(n, dtype=self.shadow_dtype, device=self.device)
         self.arena = arena
         self.refresh_shadow()
 
@@ -158,7 +159,9 @@ def attach(optimizer, models, scaler) -> bool:
     model_params = [p for m in models for p in m.parameters()]
     if len(model_params) != len(params) or any(a is not b for a, b in zip(model_params, params)):
         return False  # arena layout is defined over the full, ordered parameter list of the model
-    fused = FusedState(inner, params, scaler)
+    from .. import amp
+    shadow_dtype = torch.float16 if amp.current_state().compute == "fp16" else torch.bfloat16
+    fused = FusedState(inner, params, scaler, shadow_dtype=shadow_dtype)
     inner._fused = fused
     for m in models:
         m._ddpt_fused_optim = fused

@@ -1,4 +1,5 @@
-"""Tensor-core convolution / linear primitives (tcgen05 + TMEM + TMA), NHWC bf16.
+"""Tensor-core convolution / linear primitives (tcgen05 + TMEM + TMA), NHWC bf16 (or fp16: same kernels, the
+instruction descriptor's operand format and the epilogue's pack follow the tensors' dtype).
 
 Thin wrappers over ``_ddpt_C.conv_gemm`` / ``_ddpt_C.wgrad_gemm`` that pick the output brick
 (the M tile is a box of output pixels, see csrc/nn/conv_gemm.cu) and the N tile.  Layout
@@ -76,7 +77,7 @@ def transpose_taps(w_km: torch.Tensor, taps: int, out: Optional[torch.Tensor] = 
     """[C_out, taps*C_in] -> [C_in, taps*C_out] (bf16): the data gradient's K-major weight operand."""
     c_out, c_in = w_km.shape[0], w_km.shape[1] // taps
     if out is None:
-        out = torch.empty((c_in, taps * c_out), dtype=torch.bfloat16, device=w_km.device)
+        out = torch.empty((c_in, taps * c_out), dtype=w_km.dtype, device=w_km.device)
     require_native().transpose_taps(w_km, out, taps)
     return out
 
@@ -166,13 +167,15 @@ def stat_row_groups(out_n: int, out_h: int, out_w: int, c_out: int, block_n: Opt
 
 def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Optional[torch.Tensor] = None,
              relu: bool = False, stat_partials: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-             block_n: Optional[int] = None, out_dtype=torch.bfloat16, split_k: int = 1,
+             block_n: Optional[int] = None, out_dtype=None, split_k: int = 1,
              persistent: Optional[bool] = None, halo: Optional[bool] = None, pair: Optional[bool] = None):
     """'valid' stride-1 convolution.  x [N,H,W,C], w_km [C_out, kh*kw*C] -> y [N,Ho,Wo,C_out]."""
     ext = require_native()
     n, h, w, c = x.shape
     ho, wo = h - kh + 1, w - kw + 1
     c_out = w_km.shape[0]
+    if out_dtype is None:
+        out_dtype = x.dtype              # bf16 or fp16 activations: the output keeps the operands' 16-bit format
     if out is None:
         out = (torch.zeros if split_k > 1 else torch.empty)((n, ho, wo, c_out), dtype=out_dtype, device=x.device)
     bn = _block_n(c_out, block_n)
@@ -194,7 +197,7 @@ def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Opti
     h, w = ho + kh - 1, wo + kw - 1
     c_in = w_km.shape[1] // (kh * kw)
     if out is None:
-        out = torch.empty((n, h, w, c_in), dtype=torch.bfloat16, device=dy.device)
+        out = torch.empty((n, h, w, c_in), dtype=dy.dtype, device=dy.device)
     bn = _block_n(c_in, block_n)
     mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, pair)
     b, b_mn = w_km, True
@@ -306,7 +309,7 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, kh: int, kw: int, out: Optiona
 
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-               stat_partials: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, split_k: int = 1,
+               stat_partials: Optional[torch.Tensor] = None, out_dtype=None, split_k: int = 1,
                block_n: Optional[int] = None, persistent: Optional[bool] = None, pair: Optional[bool] = None):
     """y [M, N] = x [M, K] @ w [N, K]^T (+ bias)."""
     m, k = x.shape
@@ -327,7 +330,7 @@ def linear_fwd_splitk(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Ten
     m, k = x.shape
     n = w.shape[0]
     if out is None:
-        out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((m, n), dtype=x.dtype, device=x.device)
     slabs = _slab(x.device, split_k * m * n)[: split_k * m * n].view(split_k * m, n)
     ext.conv_gemm(x.view(1, 1, m, k), w, slabs, [1, 1, m], list(pick_box(1, 1, m)), [1, 1], 1, [0, 0], False, bias, False,
                   None, split_k, block_n, 0, True)

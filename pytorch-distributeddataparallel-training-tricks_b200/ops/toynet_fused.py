@@ -35,8 +35,8 @@ _TC_BLOCKS = ((4, 26, 64, 128, True), (8, 12, 128, 256, False), (12, 10, 256, 51
 class _Workspace:
     """Static activation / scratch buffers for one batch size (CUDA-graph friendly)."""
 
-    def __init__(self, ext, batch: int, device):
-        bf, f32 = torch.bfloat16, torch.float32
+    def __init__(self, ext, batch: int, device, act_dtype=torch.bfloat16):
+        bf, f32 = act_dtype, torch.float32
         e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=device)
         self.batch = batch
         self.y = [e(batch, 26, 26, 64), e(batch, 24, 24, 128), e(batch, 10, 10, 256), e(batch, 8, 8, 512),
@@ -85,6 +85,10 @@ class FusedToyNet:
         self.ext = require_native()
         self.model = model
         self.compute = compute
+        # activation / operand format: bf16 ("O1", "O1-fp8") or fp16 ("O1-fp16": Apex O1's precision in the reference,
+        # utils/train.py:58) -- the same kernels; csrc/nn/toynet_elementwise.cu is built for both types and the GEMMs take
+        # the format from the tensors' dtype
+        self.act_dtype = torch.float16 if compute == "fp16" else torch.bfloat16
         self.params: List[torch.nn.Parameter] = list(model.parameters())
         if len(self.params) != 22:
             raise ValueError("FusedToyNet expects the 22-parameter Toy_Net")
@@ -141,14 +145,14 @@ class FusedToyNet:
     def workspace(self, batch: int) -> _Workspace:
         ws = self._ws.get(batch)
         if ws is None:
-            ws = self._ws[batch] = _Workspace(self.ext, batch, self.device)
+            ws = self._ws[batch] = _Workspace(self.ext, batch, self.device, self.act_dtype)
         return ws
 
     def _weight_bf16(self, pidx: int) -> torch.Tensor:
         """bf16 [C_out, kh*kw*C_in] (channels-last physical order) or [N, K] for linear weights."""
         p = self.params[pidx]
         fused_opt = getattr(self.model, "_ddpt_fused_optim", None)
-        if fused_opt is not None and fused_opt.arena.channels_last:
+        if fused_opt is not None and fused_opt.arena.channels_last and fused_opt.shadow.dtype == self.act_dtype:
             return fused_opt.shadow_view(pidx).view(p.shape[0], -1)
         key = (p.data_ptr(), p._version)
         hit = self._shadow_cache.get(pidx)
@@ -157,7 +161,7 @@ class FusedToyNet:
         src = p.detach()
         if src.dim() == 4:
             src = src.permute(0, 2, 3, 1)
-        w = src.reshape(p.shape[0], -1).to(torch.bfloat16).contiguous()
+        w = src.reshape(p.shape[0], -1).to(self.act_dtype).contiguous()
         self._shadow_cache[pidx] = (key, w)
         return w
 

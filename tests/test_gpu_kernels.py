@@ -339,3 +339,40 @@ def test_conv3x3_fwd_mxfp8(ext, n, h, w, ci, co):
     part = stats.view(groups * 4, 2, co).sum(0)
     flat = want.permute(0, 2, 3, 1).reshape(-1, co)
     torch.testing.assert_close(part[0], flat.sum(0), rtol=2e-3, atol=5e-2 * math.sqrt(flat.shape[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16 operands (kind::f16 with a/b format F16): same kernels, format taken from the tensors' dtype
+# ---------------------------------------------------------------------------------------------------------------------
+def _f16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.float16)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(8, 26, 26, 64, 128), (6, 12, 12, 128, 256), (130, 10, 10, 256, 512)])
+def test_fp16_conv3x3_fwd_dgrad_wgrad(ext, gemm_flavour, n, h, w, ci, co):
+    from ddpt_b200.ops import gemm
+    x, wk = _f16(n, h, w, ci, seed=61), _f16(co, 9 * ci, scale=(9 * ci) ** -0.5, seed=62)
+    dy = _f16(n, h - 2, w - 2, co, seed=63)
+    wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    y, _ = gemm.conv_fwd(x, wk, 3, 3)
+    assert y.dtype == torch.float16
+    assert _rel_err(y.permute(0, 3, 1, 2), F.conv2d(x.float().permute(0, 3, 1, 2), wt)) < 2e-3       # fp16: ~1e-3
+    dx = gemm.conv_dgrad(dy, wk, 3, 3)
+    assert dx.dtype == torch.float16
+    assert _rel_err(dx.permute(0, 3, 1, 2), F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt)) < 2e-3
+    xg = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wref = torch.zeros(co, ci, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(xg, wref).backward(dy.float().permute(0, 3, 1, 2))
+    dw = gemm.conv_wgrad(dy, x, 3, 3)
+    assert _rel_err(dw, wref.grad.permute(0, 2, 3, 1)) < 2e-3
+
+
+def test_fp16_linear_and_splitk(ext):
+    from ddpt_b200.ops import gemm
+    x, w = _f16(1024, 8192, seed=71), _f16(512, 8192, scale=8192 ** -0.5, seed=72)
+    want = x.float() @ w.float().t()
+    y, _ = gemm.linear_fwd(x, w, None, block_n=64)
+    assert y.dtype == torch.float16 and _rel_err(y, want) < 2e-3
+    y2, rows = gemm.linear_fwd_splitk(x, w, None, None, split_k=4, block_n=128)
+    assert y2.dtype == torch.float16 and _rel_err(y2, want) < 2e-3

@@ -268,3 +268,95 @@ def test_deterministic_mode_is_bit_reproducible(monkeypatch):
     p3, b3, l3 = _train_steps()
     assert float((p1 - p3).abs().max()) < 2e-2 * float(p1.abs().max())      # same trajectory up to rounding
     assert l3 == pytest.approx(l1, rel=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# native fp16 path ("O1-fp16": Apex O1's precision in the reference, utils/train.py:58)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def nets_fp16():
+    from ddpt_b200 import amp
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.ops import toynet_fused
+    from ddpt_b200.utils import same_seeds
+    amp.reset()
+    same_seeds(3)
+    ref = Toy_Net().cuda()
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+    fused = copy.deepcopy(ref)
+    assert toynet_fused.attach(fused, "fp16")
+    return ref, fused
+
+
+@pytest.mark.parametrize("batch", [64, 304])
+def test_fp16_forward_train_and_eval_match_reference(nets_fp16, batch):
+    ref, fused = nets_fp16
+    x, _ = _batch(batch)
+    ref.train(); fused.train()
+    with torch.no_grad():
+        want = ref.forward_reference(x)
+        got = fused(x)
+    assert fused._fused.act_dtype == torch.float16 and fused._fused.workspace(batch).y[1].dtype == torch.float16
+    assert _rel(got, want) < 1e-2                      # fp16 has 3 more mantissa bits than bf16 (bf16 bound: 3e-2)
+    for (k, a), (_, b) in zip(fused.state_dict().items(), ref.state_dict().items()):
+        if "running" in k:
+            torch.testing.assert_close(a, b, rtol=5e-3, atol=1e-3, msg=k)
+    ref.eval(); fused.eval()
+    with torch.no_grad():
+        assert _rel(fused(x), ref.forward_reference(x)) < 1e-2
+
+
+def test_fp16_backward_matches_reference(nets_fp16):
+    ref, fused = nets_fp16
+    x, y = _batch(128, seed=1)
+    ref.train(); fused.train()
+    # fp16 gradients need the loss scale (the reference's Apex O1 does exactly this): scale the loss, unscale the result
+    scale = 1024.0
+    F.cross_entropy(ref.forward_reference(x), y).backward()
+    (F.cross_entropy(fused(x), y) * scale).backward()
+    names = [n for n, _ in ref.named_parameters()]
+    for n, pr, pf in zip(names, ref.parameters(), fused.parameters()):
+        g = pf.grad / scale
+        assert torch.isfinite(g).all(), n
+        if n.endswith("bias") and n.split(".")[0] + "." + n.split(".")[1] in ("conv.0", "conv.3", "conv.7", "conv.10", "dense.1"):
+            assert float(g.abs().max()) < 5e-2, n
+            continue
+        assert _rel(g, pr.grad) < 0.08, (n, _rel(g, pr.grad))
+
+
+def test_fp16_step_engine_trains_with_dynamic_loss_scale():
+    """`--opt_level O1-fp16` end to end: fused fp16 kernels + CUDA-graph engine + dynamic loss scaling; trains like bf16."""
+    import torch.nn as nn2
+    from ddpt_b200 import amp, ops
+    from ddpt_b200.models import Toy_Net
+    from ddpt_b200.optim import SGD, Lookahead
+    from ddpt_b200.utils import same_seeds
+    losses = {}
+    for level in ("O1-fp16", "O1"):
+        amp.reset(); same_seeds(5)
+        model = Toy_Net().cuda()
+        opt = Lookahead(SGD(model.parameters(), lr=0.5, momentum=0.9, nesterov=True), k=5, alpha=0.5)
+        model, opt = amp.initialize(model, optimizers=opt, opt_level=level)
+        assert model._fused.act_dtype == (torch.float16 if level == "O1-fp16" else torch.bfloat16)
+        assert opt.optimizer._fused.shadow.dtype == model._fused.act_dtype
+        assert ops.attach_step_engine(model, nn2.CrossEntropyLoss(), opt)
+        eng = model._ddpt_step_engine
+        g = torch.Generator(device="cuda").manual_seed(5)
+        model.train()
+        out = []
+        for it in range(24):
+            x = torch.randint(0, 256, (256, 1, 28, 28), device="cuda", generator=g, dtype=torch.uint8)
+            y = (x.float().mean((1, 2, 3)) > 127.5).long() + 2 * (x[:, 0, 0, 0] > 127).long()
+            eng.begin_pass(); eng.run(x, y, True)
+            loss_sum, _, seen = eng.end_pass()
+            out.append(loss_sum / seen * 256)
+        losses[level] = out
+        scale = amp.current_state().scaler.state.tolist()
+        assert scale[0] >= 1.0 and eng.graph_replays >= 20
+        amp.reset()
+    assert losses["O1-fp16"][-1] < 0.75 * losses["O1-fp16"][0], losses["O1-fp16"]
+    for a, b in zip(losses["O1-fp16"][:6], losses["O1"][:6]):
+        assert a == pytest.approx(b, rel=0.05, abs=0.02)
