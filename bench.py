@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--comm", default="fused", choices=("fused", "auto", "pg"),
                     help="gradient all-reduce back end at N>1: fused = our NVLink kernels (hard failure if unavailable)")
     ap.add_argument("--comm_wire", default="fp32", choices=("fp32", "bf16"))
-    ap.add_argument("--opt_level", default="O1", choices=("O1", "O1-fp8"),
+    ap.add_argument("--opt_level", default="O1", choices=("O1", "O1-fp16", "O1-fp8"),
                     help="O1: bf16 (headline).  O1-fp8: conv.7/conv.10/dense.1 forward on block-scaled fp8 tensor cores")
     ap.add_argument("--skip_e2e", action="store_true", help="experiments only: device-timed loop, no end-to-end loops")
     ap.add_argument("--census", default=None, help="write a per-step kernel census (CUPTI) of our arm to this JSON file")
@@ -311,7 +311,7 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.opt_level == "O1" else "bf16 + mxfp8 forward GEMMs",
+            "dtype": {"O1": "bf16", "O1-fp16": "fp16"}.get(args.opt_level, "bf16 + mxfp8 forward GEMMs"),
             "data": "synthetic uint8 1x28x28, random-init weights", "impl": "ours",
             "config": {"model": "Toy_Net", "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
                        "parallelism": f"dp{world}", "amp": args.opt_level + " + dynamic loss scale",

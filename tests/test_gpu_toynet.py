@@ -310,21 +310,31 @@ def test_fp16_forward_train_and_eval_match_reference(nets_fp16, batch):
 
 
 def test_fp16_backward_matches_reference(nets_fp16):
+    """Same yardstick as the bf16 test: a torch fp16-autocast run of the network (BatchNorm-backward cancellations
+    dominate the distance from fp32, not the storage format)."""
     ref, fused = nets_fp16
+    auto = copy.deepcopy(ref)
     x, y = _batch(128, seed=1)
-    ref.train(); fused.train()
+    ref.train(); fused.train(); auto.train()
     # fp16 gradients need the loss scale (the reference's Apex O1 does exactly this): scale the loss, unscale the result
     scale = 1024.0
     F.cross_entropy(ref.forward_reference(x), y).backward()
     (F.cross_entropy(fused(x), y) * scale).backward()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = auto.forward_reference(x)
+    (F.cross_entropy(out.float(), y) * scale).backward()
     names = [n for n, _ in ref.named_parameters()]
-    for n, pr, pf in zip(names, ref.parameters(), fused.parameters()):
-        g = pf.grad / scale
+    bad = {}
+    for n, pr, pf, pa in zip(names, ref.parameters(), fused.parameters(), auto.parameters()):
+        g, ga = pf.grad / scale, pa.grad / scale
         assert torch.isfinite(g).all(), n
         if n.endswith("bias") and n.split(".")[0] + "." + n.split(".")[1] in ("conv.0", "conv.3", "conv.7", "conv.10", "dense.1"):
             assert float(g.abs().max()) < 5e-2, n
             continue
-        assert _rel(g, pr.grad) < 0.08, (n, _rel(g, pr.grad))
+        e_fused, e_auto = _rel(g, pr.grad), _rel(ga, pr.grad)
+        if e_fused > 1.35 * e_auto + 0.01:
+            bad[n] = (e_fused, e_auto)
+    assert not bad, bad
 
 
 def test_fp16_step_engine_trains_with_dynamic_loss_scale():
