@@ -1,6 +1,6 @@
 """Launch one Toy_Net convolution GEMM a few times (for `ncu -k regex:... -s 2 -c 1`).
 
-    python benchmarks/run_one_conv.py conv.10 fwd pair
+    python benchmarks/run_one_conv.py conv.10 fwd pair | default
 """
 import os
 import sys
@@ -21,6 +21,8 @@ def main():
     wk = (torch.randn(co, 9 * ci, device="cuda") * 0.05).bfloat16()
     dy = torch.randn(batch, h - 2, w - 2, co, device="cuda").bfloat16()
     kw = dict(persistent=flavour != "per_tile", halo=flavour == "halo", pair=flavour == "pair")
+    if flavour == "default":        # what the fused model's step launches
+        kw = {}
     for _ in range(4):
         if op == "fwd":
             gemm.conv_fwd(x, wk, 3, 3, **kw)

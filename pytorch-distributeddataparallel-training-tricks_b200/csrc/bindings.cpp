@@ -188,6 +188,8 @@ int64_t conv_gemm(at::Tensor a, at::Tensor b, at::Tensor out, std::vector<int64_
     TORCH_CHECK(stat_partials->numel() >= groups * 8 * p.n_total, "stat_partials too small: need ", groups * 8 * p.n_total);
     TORCH_CHECK(split_k <= 1, "statistics need the full reduction in one CTA");
   }
+  // mode 4: 3x3 data gradient with 64 input channels, filter columns merged into N (conv_dgrad_kwmerge.cu)
+  if (mode == 4) return ddpt::launch_conv_dgrad_kwmerge(p, current_stream());
   // mode: 0 = one CTA per tile (split-K capable), 1 = persistent, 2 = persistent + halo reuse
   if (mode == 2 && split_k <= 1) return ddpt::launch_conv_gemm_halo(p, (int)block_n, current_stream());
   // mode 3: persistent kernel as CTA pairs (tcgen05 cta_group::2, 256-row tiles)

@@ -55,6 +55,10 @@ int launch_conv_gemm_persistent(const ConvGemmProblem& p, int block_n, cudaStrea
 // Halo-reuse variant: the activation brick (+halo) is loaded once per channel chunk and every filter tap is a
 // shifted descriptor view; requires box_w == 8 and box_h * box_n <= 16.  Same return convention as persistent.
 int launch_conv_gemm_halo(const ConvGemmProblem& p, int block_n, cudaStream_t stream);
+// 3x3 data gradient with 64 input channels (n_total == 64, MN-major weights, tap_sign == -1, C_out 64 or 128): the three
+// filter columns are merged into the MMA's N dimension (128 x 192 instructions) and summed with a pixel shift in the
+// epilogue; a_h_off == a_w_off is the forward convolution's padding.  See csrc/nn/conv_dgrad_kwmerge.cu.
+int launch_conv_dgrad_kwmerge(const ConvGemmProblem& p, cudaStream_t stream);
 
 // Fold `splits` fp32 slabs [rows, cols] (stride slab_stride elements) in split order into a bf16 matrix and, optionally,
 // BatchNorm column statistics as partial rows [blocks][2][cols] (returns the number of rows written) -- the second half

@@ -187,17 +187,33 @@ def conv_fwd(x: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, bias: Option
 
 def conv_dgrad(dy: torch.Tensor, w_km: torch.Tensor, kh: int, kw: int, out: Optional[torch.Tensor] = None,
                block_n: Optional[int] = None, persistent: Optional[bool] = None, halo: Optional[bool] = None,
-               pair: Optional[bool] = None, w_t: Optional[torch.Tensor] = None):
-    """Data gradient of the 'valid' stride-1 convolution.  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in].
+               pair: Optional[bool] = None, w_t: Optional[torch.Tensor] = None, kwmerge: Optional[bool] = None,
+               pad: int = 0):
+    """Data gradient of the stride-1 convolution ('valid' unless ``pad``).  dy [N,Ho,Wo,C_out] -> dx [N,H,W,C_in].
 
     ``w_t`` (optional, :func:`transpose_taps` of ``w_km``): K-major weights [C_in, taps*C_out]; with 64 input channels
-    they let the data gradient run on CTA pairs (DDPT_DGRAD64_PAIR=1)."""
+    they let the data gradient run on CTA pairs (DDPT_DGRAD64_PAIR=1).
+
+    ``kwmerge`` (default: on when it applies -- 3x3, 64 input channels, 64 / 128 output channels, no explicit flavour):
+    the kernel of csrc/nn/conv_dgrad_kwmerge.cu, one 128 x 192 MMA per filter ROW instead of three 128 x 64 ones."""
     ext = require_native()
     n, ho, wo, c_out = dy.shape
-    h, w = ho + kh - 1, wo + kw - 1
+    h, w = ho + kh - 1 - 2 * pad, wo + kw - 1 - 2 * pad
     c_in = w_km.shape[1] // (kh * kw)
     if out is None:
         out = torch.empty((n, h, w, c_in), dtype=dy.dtype, device=dy.device)
+    can_merge = kh == 3 and kw == 3 and c_in == 64 and c_out in (64, 128)
+    if kwmerge is None:
+        kwmerge = (can_merge and block_n is None and persistent is None and halo is None and pair is None
+                   and os.environ.get("DDPT_DGRAD_KWMERGE", "1") != "0")
+    if kwmerge:
+        if not can_merge:
+            raise ValueError("kwmerge data gradient: 3x3 filter, 64 input channels, 64 or 128 output channels")
+        ext.conv_gemm(dy, w_km, out.view(n * h * w, c_in), [n, h, w], [1, 4, 30], [3, 3], -1, [pad, pad], True,
+                      None, False, None, 1, 64, 4)
+        return out
+    if pad:
+        raise ValueError("padded data gradients exist only in the kwmerge kernel")
     bn = _block_n(c_in, block_n)
     mode, box = _gemm_mode(persistent, halo, (n, h, w), kh, kw, c_out, c_in, bn, pair)
     b, b_mn = w_km, True

@@ -22,6 +22,7 @@ def gemm_flavour(request, monkeypatch):
     monkeypatch.setenv("DDPT_GEMM_PERSISTENT", "0" if request.param == "per_tile" else "1")
     monkeypatch.setenv("DDPT_GEMM_HALO", "force" if request.param == "halo" else "0")
     monkeypatch.setenv("DDPT_GEMM_PAIR", "1" if request.param == "pair" else "0")
+    monkeypatch.setenv("DDPT_DGRAD_KWMERGE", "0")      # the merged-column data gradient has its own tests below
     return request.param
 
 
@@ -376,3 +377,50 @@ def test_fp16_linear_and_splitk(ext):
     assert y.dtype == torch.float16 and _rel_err(y, want) < 2e-3
     y2, rows = gemm.linear_fwd_splitk(x, w, None, None, split_k=4, block_n=128)
     assert y2.dtype == torch.float16 and _rel_err(y2, want) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3x3 data gradient with 64 input channels: filter columns merged into the MMA's N dimension (conv_dgrad_kwmerge.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,co,pad", [(5, 26, 26, 128, 0),      # Toy_Net conv.3 (one 30-column tile, 7 row bricks)
+                                          (3, 9, 37, 64, 0),        # two column tiles, a ragged last one
+                                          (2, 4, 30, 128, 0),       # exactly one tile per image
+                                          (2, 61, 64, 64, 0),       # three column tiles
+                                          (3, 14, 14, 64, 1),       # 'same' convolution (ResNet-style): padding = origin shift
+                                          (2, 33, 31, 128, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_dgrad_kwmerge_matches_conv_transpose(ext, n, h, w, co, pad, dtype):
+    """dx [n, h, w, 64] from dy [n, h - 2 + 2 pad, w - 2 + 2 pad, co]; reference: fp32 conv_transpose2d."""
+    from ddpt_b200.ops import gemm
+    ci = 64
+    ho, wo = h - 2 + 2 * pad, w - 2 + 2 * pad
+    g = torch.Generator(device="cuda").manual_seed(81)
+    dy = torch.randn(n, ho, wo, co, device="cuda", generator=g).to(dtype)
+    wk = (torch.randn(co, 9 * ci, device="cuda", generator=g) * (9 * co) ** -0.5).to(dtype)
+    wt = wk.float().view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    want = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt, padding=pad)
+    out = torch.full((n, h, w, ci), float("nan"), device="cuda", dtype=dtype)
+    got = gemm.conv_dgrad(dy, wk, 3, 3, out=out, kwmerge=True, pad=pad)
+    assert got.dtype == dtype and torch.isfinite(got.float()).all()       # every output pixel written, none twice-shifted
+    assert _rel_err(got.permute(0, 3, 1, 2), want) < (2e-3 if dtype == torch.float16 else 6e-3)
+    if pad == 0:        # same answer as the generic kernels
+        other = gemm.conv_dgrad(dy, wk, 3, 3, kwmerge=False)
+        assert _rel_err(got, other) < 6e-3
+    again = gemm.conv_dgrad(dy, wk, 3, 3, kwmerge=True, pad=pad)
+    assert torch.equal(got, again)                                        # no atomics: bit-reproducible
+
+
+def test_conv_dgrad_kwmerge_is_the_default_for_conv3(ext, monkeypatch):
+    from ddpt_b200.ops import gemm
+    calls = []
+    real = ext.conv_gemm
+    class Spy:
+        def __getattr__(self, name):
+            if name == "conv_gemm":
+                return lambda *a, **k: (calls.append(a[-1]), real(*a, **k))[1]
+            return getattr(ext, name)
+    monkeypatch.setattr(gemm, "require_native", lambda: Spy())
+    monkeypatch.delenv("DDPT_DGRAD_KWMERGE", raising=False)
+    dy, wk = _bf16(4, 24, 24, 128, seed=5), _bf16(128, 576, scale=0.03, seed=6)
+    gemm.conv_dgrad(dy, wk, 3, 3)
+    assert calls == [4]
