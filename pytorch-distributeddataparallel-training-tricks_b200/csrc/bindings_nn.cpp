@@ -1,4 +1,5 @@
 // Bindings for the bandwidth-bound Toy_Net kernels (csrc/nn/toynet_elementwise.cu).
+#include <cstdlib>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -55,7 +56,7 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
 
 void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10::optional<at::Tensor> partials,
                  c10::optional<at::Tensor> bn_y, c10::optional<at::Tensor> bn_g, c10::optional<at::Tensor> bn_coeffs,
-                 c10::optional<at::Tensor> bn_bwd_coef) {
+                 c10::optional<at::Tensor> bn_bwd_coef, c10::optional<bool> tensor_core) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
   need_act(dy, dy, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
   const int batch = (int)(x.numel() / (28 * 28));
@@ -75,6 +76,15 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
     TORCH_CHECK(bn_y->numel() == dy.numel() && bn_g->numel() == dy.numel() && bn_coeffs->numel() >= 4 * 64 && bn_bwd_coef->numel() >= 3 * 64);
     const float* co = bn_coeffs->data_ptr<float>();
     bn = ddpt::Conv0BnFuse{bn_y->data_ptr(), bn_g->data_ptr(), co, co + 64, co + 128, co + 192, bn_bwd_coef->data_ptr<float>()};
+  }
+  // tensor-core variant (conv0_wgrad_tc.cu): opt-in (argument, or DDPT_CONV0_WGRAD_TC=1).  Measured inside the graphed step
+  // it is no faster than the CUDA-core kernel (129 vs 114 us, profiles/step_timeline_r2.txt): producing the swizzled
+  // operands costs the threads as many instructions as the 80 FFMA per gradient vector they replace.
+  static const bool env_tc = std::getenv("DDPT_CONV0_WGRAD_TC") != nullptr && std::atoi(std::getenv("DDPT_CONV0_WGRAD_TC")) != 0;
+  if (tensor_core.has_value() ? *tensor_core : env_tc) {
+    ddpt::launch_conv0_wgrad_tc(x.data_ptr(), x.scalar_type() == at::kByte, dy.data_ptr(), is_half(dy) ? 1 : 0,
+                                dw.data_ptr<float>(), db.data_ptr<float>(), part, batch, bn, cur());
+    return;
   }
   if (is_half(dy))
     ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, hf(dy), dw.data_ptr<float>(),
@@ -334,7 +344,7 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("conv0_fwd", &conv0_fwd);
   m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none(),
         py::arg("bn_y") = py::none(), py::arg("bn_g") = py::none(), py::arg("bn_coeffs") = py::none(),
-        py::arg("bn_bwd_coef") = py::none());
+        py::arg("bn_bwd_coef") = py::none(), py::arg("tensor_core") = py::none());
   m.def("transpose_taps", &transpose_taps);
   m.def("det_workspace_floats", []() {     // fp32 elements of the deterministic-mode partial-row workspace
     return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,

@@ -33,6 +33,10 @@ struct Conv0BnFuse {
 int conv0_wgrad_partial_rows();
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
                         int batch, const Conv0BnFuse& bn, cudaStream_t s);
+// Same contract on the tensor cores (csrc/nn/conv0_wgrad_tc.cu): dW^T = dy^T . [patches | 1] as 128 x 32 x 16 tcgen05.mma
+// over operands the threads write to shared memory (dy derived from y0 / g on the fly when bn.y is set); the default.
+void launch_conv0_wgrad_tc(const void* x, int x_is_u8, const void* dy, int fp16, float* dw, float* db, float* partials,
+                           int batch, const Conv0BnFuse& bn, cudaStream_t s);
 
 // ---- BatchNorm (training) ---------------------------------------------------------------------------
 struct BnCoeffs {          // all float [C]

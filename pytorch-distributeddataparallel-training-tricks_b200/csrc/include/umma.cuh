@@ -120,6 +120,20 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- warpgroup register reallocation ---------------------------------------------------------------------
+// All four warps of a warpgroup execute these together.  dec releases registers to the SM's pool at once; inc blocks
+// until the pool holds enough (i.e. until the other warpgroups have released theirs).
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  static_assert(kRegs % 8 == 0 && kRegs >= 24 && kRegs <= 256, "setmaxnreg: multiple of 8 in [24, 256]");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  static_assert(kRegs % 8 == 0 && kRegs >= 24 && kRegs <= 256, "setmaxnreg: multiple of 8 in [24, 256]");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {

@@ -30,8 +30,13 @@ using namespace umma;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 320;
+// Three warpgroups: warps 0..3 control (0: TMA producer, 1: MMA issuer, 2: second issuer when NI == 2, 3: idle), warps
+// 4..11 epilogue.  After the setup the control group gives registers back (setmaxnreg.dec) and the epilogue groups take
+// them (setmaxnreg.inc): the epilogue's per-thread BatchNorm accumulators need ~200 registers, the single-lane roles ~50.
+constexpr int kThreads = 384;
 constexpr int kEpilogueWarps = 8;
+constexpr int kFirstEpilogueWarp = 4;
+constexpr int kControlRegs = 104, kEpilogueRegs = 200;     // 128 x 104 + 256 x 200 = 64512 <= 65536
 constexpr int kMaxSmem = 227 * 1024;
 
 struct HaloArgs {
@@ -52,6 +57,24 @@ struct HaloArgs {
   int fp16;                         // operands and 16-bit outputs are fp16 instead of bf16
 };
 
+// Column sums over the 32 rows a warp holds (one row per lane, 32 columns per lane): a transposing butterfly -- after
+// log2(32) exchange levels lane L holds, in element 0, the sum of column L over all 32 lanes (31 shuffles per array).
+__device__ __forceinline__ void warp_column_sums(float (&s1)[32], float (&s2)[32], int lane) {
+#pragma unroll
+  for (int width = 16; width >= 1; width >>= 1) {
+    const bool upper = (lane & width) != 0;
+#pragma unroll
+    for (int j = 0; j < width; ++j) {
+      float keep1 = upper ? s1[j + width] : s1[j];
+      float give1 = upper ? s1[j] : s1[j + width];
+      float keep2 = upper ? s2[j + width] : s2[j];
+      float give2 = upper ? s2[j] : s2[j + width];
+      s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, give1, width);
+      s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, width);
+    }
+  }
+}
+
 // NI = 2 (resident weights, BN <= 128): TWO MMA-issuing warps.  A 128 x 64 x 16 MMA is 32 tensor cycles, less than one
 // in-order thread needs to build and issue it (profiles/ncu_gemm_v2.txt: conv.3 data gradient, tensor pipe 39 % active,
 // the issuing lane 65 % busy with descriptor arithmetic + UTCHMMA).  Issuer j takes every second activation brick
@@ -65,7 +88,7 @@ struct HaloArgs {
 // instructions of runtime tap arithmetic and descriptor encoding the generic loop spends -- on 64-column tiles (32
 // tensor cycles per MMA) that arithmetic, not the tensor pipe, set the pace (tensor pipe 39 % active).
 template <int BN, bool B_MN, bool B_RES, int NI, int KC>
-__global__ void __launch_bounds__(kThreads + 32 * (NI - 1), 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const HaloArgs args, const int num_m_tiles, const int num_n_tiles) {
   constexpr int kBStageBytes = BN * kBlockK * 2;
@@ -120,6 +143,8 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   };
 
+  if (warp < kFirstEpilogueWarp) {
+  reg_dealloc<kControlRegs>();      // the whole control warpgroup, before its warps split into roles
   if (warp == 0) {
     // ===== TMA producer: one halo brick per (tile, channel chunk); weights resident or streamed per tap =====
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
@@ -162,9 +187,9 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
       }
     }
-  } else if (warp == 1 || warp == 2 + kEpilogueWarps) {
+  } else if (warp == 1 || (NI == 2 && warp == 2)) {
     // ===== MMA issuer(s): every tap is a shifted view of the halo brick =====
-    const int me = warp == 1 ? 0 : 1;                       // issuer index (NI == 2: warp 10 is the second issuer)
+    const int me = warp == 1 ? 0 : 1;                       // issuer index (NI == 2: warp 2 is the second issuer)
     if (elect_one()) {   // one elected lane: operands stay in uniform registers (no per-lane waterfall)
       int a_s = 0, b_s = 0;
       uint32_t a_phase = 0, b_phase = 0, t = 0, brick = 0;
@@ -252,10 +277,12 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         mma_commit(&tmem_full[acc]);
       }
     }
+  }
   } else {
-    // ===== epilogue: row m = group (h, n) x 8 pixels; quadrant = warp & 3, column half = (warp - 2) >> 2 =====
+    reg_alloc<kEpilogueRegs>();
+    // ===== epilogue: row m = group (h, n) x 8 pixels; quadrant = warp & 3, column half = (warp - 4) >> 2 =====
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - kFirstEpilogueWarp) >> 2;
     const int row = quad * 32 + lane;
     const int grp = row >> 3, dw = row & 7;
     const int dh = grp / args.box_n, dn = grp - dh * args.box_n;
@@ -263,6 +290,17 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     float acc_s1[kChunksPerWarp], acc_s2[kChunksPerWarp];
 #pragma unroll
     for (int cc = 0; cc < kChunksPerWarp; ++cc) acc_s1[cc] = acc_s2[cc] = 0.f;
+    // BatchNorm statistics of forward tiles up to 128 columns wide: every thread keeps running sums of ITS row's values
+    // for its 32 / 64 columns across all tiles of the CTA, and the cross-lane fold runs once per CTA at the end.  The
+    // per-tile butterfly (124 shuffles + 250 selects per warp and tile) made conv.3's forward EPILOGUE-bound: 42 M warp
+    // instructions, shuffle pipe saturated, 7200 cycles per tile against 2304 cycles of MMAs, tensor pipe 33 % busy
+    // (profiles/ncu_r2_fwd3_halo_step.txt).  128 fp32 accumulators fit next to the 32 live tile values (200 registers after setmaxnreg).
+    constexpr bool kRegStats = !B_MN && BN <= 128 && NI == 1;
+    constexpr int kRegCols = kRegStats ? kChunksPerWarp * 32 : 1;
+    float racc1[kRegCols], racc2[kRegCols];
+#pragma unroll
+    for (int j = 0; j < kRegCols; ++j) racc1[j] = racc2[j] = 0.f;
+    const bool want_stats = args.stat_partials != nullptr || args.stat_accum != nullptr;
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int tile_m = tile / num_n_tiles, tile_n = tile - tile_m * num_n_tiles;
@@ -275,7 +313,7 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase, 47);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll (kRegStats ? kChunksPerWarp : 1)
       for (int cc = 0; cc < kChunksPerWarp; ++cc) {
         const int c = half * kChunksPerWarp + cc;
         uint32_t v[32];
@@ -295,28 +333,26 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
         }
-        if (args.stat_partials != nullptr || args.stat_accum != nullptr) {
-          float s1[32], s2[32];
+        if (want_stats) {
+          if constexpr (kRegStats) {
+            if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s1[j] = valid ? f[j] : 0.f;
-            s2[j] = s1[j] * s1[j];
-          }
-#pragma unroll
-          for (int width = 16; width >= 1; width >>= 1) {
-            const bool upper = (lane & width) != 0;
-#pragma unroll
-            for (int j = 0; j < width; ++j) {
-              float keep1 = upper ? s1[j + width] : s1[j];
-              float give1 = upper ? s1[j] : s1[j + width];
-              float keep2 = upper ? s2[j + width] : s2[j];
-              float give2 = upper ? s2[j] : s2[j + width];
-              s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, give1, width);
-              s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, give2, width);
+              for (int j = 0; j < 32; ++j) {
+                racc1[cc * 32 + j] += f[j];
+                racc2[cc * 32 + j] = fmaf(f[j], f[j], racc2[cc * 32 + j]);
+              }
             }
+          } else {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1[j] = valid ? f[j] : 0.f;
+              s2[j] = s1[j] * s1[j];
+            }
+            warp_column_sums(s1, s2, lane);
+            acc_s1[cc] += s1[0];
+            acc_s2[cc] += s2[0];
           }
-          acc_s1[cc] += s1[0];
-          acc_s2[cc] += s2[0];
         }
         if (args.relu) {
 #pragma unroll
@@ -348,6 +384,19 @@ conv_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if constexpr (kRegStats) {
+      if (want_stats) {
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = racc1[cc * 32 + j]; s2[j] = racc2[cc * 32 + j]; }
+          warp_column_sums(s1, s2, lane);
+          acc_s1[cc] = s1[0];
+          acc_s2[cc] = s2[0];
+        }
+      }
     }
     if (args.stat_accum != nullptr) {
       const int my_tile_n = blockIdx.x % num_n_tiles;
@@ -462,7 +511,7 @@ int launch_impl(const ConvGemmProblem& p, cudaStream_t stream) {
       // "my brick has landed" from "the brick two laps ago had" when it runs ahead of the other issuer (seen as a sporadic
       // launch failure in the first version).
       a.a_stages &= ~1;
-      run(conv_gemm_halo_kernel<BN, B_MN, true, 2, 0>, kThreads + 32);
+      run(conv_gemm_halo_kernel<BN, B_MN, true, 2, 0>, kThreads);
       DDPT_CUDA_CHECK(cudaGetLastError());
       return p.stat_partials != nullptr ? grid : tiles_m;
     }

@@ -28,6 +28,7 @@ from __future__ import annotations
 from typing import Callable, Optional
 
 import torch
+from ..utils.capture import graph_capture
 
 from .. import amp
 
@@ -60,7 +61,7 @@ class GraphedTrainStep:
             if self._fused is not None:
                 self._fused.prepare_for_capture(self._sgd, self._lookahead)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            with graph_capture(self.graph, stream=side):
                 self._body()
 
     def _body(self) -> None:

@@ -18,6 +18,7 @@ from __future__ import annotations
 from typing import Dict, Optional, Tuple
 
 import torch
+from ..utils.capture import graph_capture
 import torch.nn as nn
 
 
@@ -194,7 +195,7 @@ class StepEngine:
                 self.fused_opt.prepare_for_capture(self.sgd, self.lookahead)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=self.capture_stream):
+            with graph_capture(graph, stream=self.capture_stream):
                 body(sx, st)
             self._graphs[key] = graph
             graph.replay()

@@ -424,3 +424,72 @@ def test_conv_dgrad_kwmerge_is_the_default_for_conv3(ext, monkeypatch):
     dy, wk = _bf16(4, 24, 24, 128, seed=5), _bf16(128, 576, scale=0.03, seed=6)
     gemm.conv_dgrad(dy, wk, 3, 3)
     assert calls == [4]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conv.0 weight gradient: the CUDA-core kernel (default) and the tensor-core variant (conv0_wgrad_tc.cu, opt-in)
+# ---------------------------------------------------------------------------------------------------------------------
+def _conv0_wgrad_reference(x_f, dy_f):
+    """dW [64, 9], db [64] of Conv2d(1, 64, 3) from x [B, 28, 28] fp32 and dy [B, 26, 26, 64] fp32."""
+    xg = x_f.view(-1, 1, 28, 28)
+    w = torch.zeros(64, 1, 3, 3, device="cuda", requires_grad=True)
+    b = torch.zeros(64, device="cuda", requires_grad=True)
+    F.conv2d(xg, w, b).backward(dy_f.permute(0, 3, 1, 2))
+    return w.grad.view(64, 9), b.grad
+
+
+@pytest.mark.parametrize("batch", [3, 333])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("u8", [True, False])
+@pytest.mark.parametrize("det", [False, True])
+@pytest.mark.parametrize("tc", [True, False])
+def test_conv0_wgrad_kernels(ext, batch, dtype, u8, det, tc):
+    g = torch.Generator(device="cuda").manual_seed(91)
+    if u8:
+        x = torch.randint(0, 256, (batch, 28, 28), device="cuda", generator=g, dtype=torch.uint8)
+        x_f = x.float() / 255.0
+    else:
+        x = torch.randn(batch, 28, 28, device="cuda", generator=g)
+        x_f = x
+    dy = (torch.randn(batch, 26, 26, 64, device="cuda", generator=g) * 0.1).to(dtype)
+    dw, db = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
+    part = torch.zeros(ext.det_workspace_floats(), device="cuda") if det else None
+    ext.conv0_wgrad(x, dy, dw, db, part, tensor_core=tc)
+    want_w, want_b = _conv0_wgrad_reference(x_f, dy.float())
+    # dy is exact (already 16-bit); on the tensor cores x goes in as a 16-bit value + its rounding remainder:
+    # fp32-accumulation accuracy either way
+    assert _rel_err(dw.view(64, 9), want_w) < 2e-5, _rel_err(dw.view(64, 9), want_w)
+    assert _rel_err(db, want_b) < 2e-5
+    if det:
+        dw2, db2 = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
+        ext.conv0_wgrad(x, dy, dw2, db2, part, tensor_core=tc)
+        assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("tc", [True, False])
+def test_conv0_wgrad_fused_bn_apply(ext, dtype, tc):
+    """With the BatchNorm-backward apply folded in: dy = c1 * dz + k0 - k1 * y0, dz = g where relu(bn(y0)) > 0."""
+    batch = 200
+    g = torch.Generator(device="cuda").manual_seed(92)
+    x = torch.randint(0, 256, (batch, 28, 28), device="cuda", generator=g, dtype=torch.uint8)
+    y0 = torch.randn(batch, 26, 26, 64, device="cuda", generator=g).to(dtype)
+    gin = (torch.randn(batch, 26, 26, 64, device="cuda", generator=g) * 0.05).to(dtype)
+    coeffs = torch.empty(4, 64, device="cuda")
+    coeffs[0].uniform_(0.5, 1.5, generator=g); coeffs[1].uniform_(-0.5, 0.5, generator=g)          # scale, shift
+    coeffs[2].uniform_(-0.2, 0.2, generator=g); coeffs[3].uniform_(0.8, 1.2, generator=g)          # mean, invstd
+    bcoef = torch.empty(3, 64, device="cuda")
+    bcoef[0].uniform_(0.5, 1.5, generator=g); bcoef[1].uniform_(-0.01, 0.01, generator=g); bcoef[2].uniform_(-0.01, 0.01, generator=g)
+    sc, sh, mu, istd = coeffs
+    c1, c2, c3 = bcoef
+    yf, gf = y0.float(), gin.float()
+    dz = torch.where(yf * sc + sh > 0, gf, torch.zeros_like(gf))
+    k1 = c1 * istd * c3
+    k0 = k1 * mu - c1 * c2
+    dy = (c1 * dz + k0 - k1 * yf).to(dtype).float()                 # the kernel rounds dy to the activation type
+    want_w, want_b = _conv0_wgrad_reference(x.float() / 255.0, dy)
+    dw, db = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
+    ext.conv0_wgrad(x, torch.empty_like(y0), dw, db, None, y0, gin, coeffs.view(-1), bcoef.view(-1), tensor_core=tc)
+    # fmaf association differs from the torch expression by an ulp of the 16-bit rounding on a few elements
+    assert _rel_err(dw.view(64, 9), want_w) < 2e-3, _rel_err(dw.view(64, 9), want_w)
+    assert _rel_err(db, want_b) < 2e-3
