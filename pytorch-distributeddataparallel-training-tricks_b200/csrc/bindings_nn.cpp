@@ -97,7 +97,8 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
 // coeffs: float [4][C] = scale, shift, mean, invstd
 void bn_finalize(at::Tensor partials, int64_t num_partials, double count, at::Tensor gamma, at::Tensor beta,
                  double eps, double momentum, at::Tensor coeffs, c10::optional<at::Tensor> running_mean,
-                 c10::optional<at::Tensor> running_var, c10::optional<at::Tensor> nbt) {
+                 c10::optional<at::Tensor> running_var, c10::optional<at::Tensor> nbt,
+                 c10::optional<at::Tensor> conv_bias) {
   need(partials, at::kFloat, "partials"); need(gamma, at::kFloat, "gamma"); need(beta, at::kFloat, "beta");
   need(coeffs, at::kFloat, "coeffs");
   const int c = (int)gamma.numel();
@@ -105,16 +106,18 @@ void bn_finalize(at::Tensor partials, int64_t num_partials, double count, at::Te
   c10::cuda::CUDAGuard g(gamma.device());
   float* co = coeffs.data_ptr<float>();
   ddpt::BnCoeffs out{co, co + c, co + 2 * c, co + 3 * c};
+  const float* cb = nullptr;
+  if (conv_bias.has_value()) { need(*conv_bias, at::kFloat, "conv_bias"); TORCH_CHECK(conv_bias->numel() == c); cb = conv_bias->data_ptr<float>(); }
   long long* n = nullptr;
   if (nbt.has_value()) { TORCH_CHECK(nbt->scalar_type() == at::kLong); n = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
   ddpt::launch_bn_finalize(partials.data_ptr<float>(), (int)num_partials, c, count, gamma.data_ptr<float>(),
                            beta.data_ptr<float>(), (float)eps, (float)momentum, out,
                            running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
-                           running_var.has_value() ? running_var->data_ptr<float>() : nullptr, n, cur());
+                           running_var.has_value() ? running_var->data_ptr<float>() : nullptr, n, cb, cur());
 }
 
 void bn_eval_coeffs(at::Tensor gamma, at::Tensor beta, at::Tensor running_mean, at::Tensor running_var, double eps,
-                    at::Tensor coeffs) {
+                    at::Tensor coeffs, c10::optional<at::Tensor> conv_bias) {
   need(gamma, at::kFloat, "gamma"); need(beta, at::kFloat, "beta"); need(running_mean, at::kFloat, "running_mean");
   need(running_var, at::kFloat, "running_var"); need(coeffs, at::kFloat, "coeffs");
   const int c = (int)gamma.numel();
@@ -122,7 +125,8 @@ void bn_eval_coeffs(at::Tensor gamma, at::Tensor beta, at::Tensor running_mean, 
   c10::cuda::CUDAGuard g(gamma.device());
   float* co = coeffs.data_ptr<float>();
   ddpt::launch_bn_eval_coeffs(gamma.data_ptr<float>(), beta.data_ptr<float>(), running_mean.data_ptr<float>(),
-                              running_var.data_ptr<float>(), (float)eps, c, co, co + c, cur());
+                              running_var.data_ptr<float>(), (float)eps, c, co, co + c,
+                              conv_bias.has_value() ? conv_bias->data_ptr<float>() : nullptr, cur());
 }
 
 // accum (optional, fp64 [2][C]): fused statistics -- the kernel derives scale/shift itself, writes them (+ mean, invstd)
@@ -350,8 +354,11 @@ void ddpt_bind_nn(pybind11::module_& m) {
     return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,
                                       (int64_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * ddpt::head_partial_cols());
   });
-  m.def("bn_finalize", &bn_finalize);
-  m.def("bn_eval_coeffs", &bn_eval_coeffs);
+  m.def("bn_finalize", &bn_finalize, py::arg("partials"), py::arg("num_partials"), py::arg("count"), py::arg("gamma"),
+        py::arg("beta"), py::arg("eps"), py::arg("momentum"), py::arg("coeffs"), py::arg("running_mean") = py::none(),
+        py::arg("running_var") = py::none(), py::arg("nbt") = py::none(), py::arg("conv_bias") = py::none());
+  m.def("bn_eval_coeffs", &bn_eval_coeffs, py::arg("gamma"), py::arg("beta"), py::arg("running_mean"), py::arg("running_var"),
+        py::arg("eps"), py::arg("coeffs"), py::arg("conv_bias") = py::none());
   m.def("bn_relu_pool", &bn_relu_pool, py::arg("y"), py::arg("coeffs"), py::arg("out"), py::arg("pool"),
         py::arg("flatten_chw"), py::arg("q_out") = py::none(), py::arg("q_scale") = py::none(),
         py::arg("accum") = py::none(), py::arg("count") = 0.0, py::arg("gamma") = py::none(),

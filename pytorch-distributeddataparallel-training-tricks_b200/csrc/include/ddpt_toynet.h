@@ -71,11 +71,11 @@ struct BnFusedBwd {
 // and num_batches_tracked (int64).
 void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                         const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
-                        float* running_var, long long* num_batches_tracked, cudaStream_t s);
+                        float* running_var, long long* num_batches_tracked, const float* conv_bias, cudaStream_t s);
 // Eval mode: scale/shift from the running statistics.
 void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                            const float* running_var, float eps, int channels, float* scale, float* shift,
-                           cudaStream_t s);
+                           const float* conv_bias, cudaStream_t s);
 // a = relu(y * scale + shift), optionally followed by 2x2 max-pool; flatten_chw: write the pooled map
 // as [N][C*PH*PW] in (c, h, w) order -- torch's Flatten of an NCHW tensor -- for the first Linear.
 // q_out / q_scale (optional): also emit the activation as MXFP8 (e4m3 [same layout] + UE8M0 per 32 along the last dim)

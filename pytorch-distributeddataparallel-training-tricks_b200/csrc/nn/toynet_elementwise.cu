@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(32 * kFinGroups)
 bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int channels, double count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    BnCoeffs out, float* __restrict__ running_mean, float* __restrict__ running_var,
-                   long long* __restrict__ nbt) {
+                   long long* __restrict__ nbt, const float* __restrict__ conv_bias) {
+  // conv_bias (optional): the statistics are those of the convolution WITHOUT its bias -- the producing GEMM skipped the
+  // add (a per-channel constant in front of a BatchNorm cancels in the normalised output and in every gradient; only
+  // running_mean sees it).  mean / shift stay consistent with the stored bias-free activations.
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   __shared__ double s_sum[kFinGroups][32], s_sq[kFinGroups][32];
@@ -364,7 +367,8 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
     out.invstd[c] = invstd;
     if (running_mean != nullptr) {
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      const float batch_mean = conv_bias != nullptr ? (float)mean + conv_bias[c] : (float)mean;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * batch_mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   }
@@ -373,14 +377,15 @@ bn_finalize_kernel(const float* __restrict__ partials, int num_partials, int cha
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
-                                      int channels, float* __restrict__ scale, float* __restrict__ shift) {
+                                      int channels, float* __restrict__ scale, float* __restrict__ shift,
+                                      const float* __restrict__ conv_bias) {
   pdl_wait();      // previous kernel of the stream has completed and flushed
   pdl_trigger();   // the next kernel may be scheduled behind this one
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= channels) return;
   const float sc = gamma[c] * rsqrtf(rv[c] + eps);
   scale[c] = sc;
-  shift[c] = beta[c] - rm[c] * sc;
+  shift[c] = beta[c] - (conv_bias != nullptr ? rm[c] - conv_bias[c] : rm[c]) * sc;   // bias-free activations (see bn_finalize)
 }
 
 // Fused statistics (BnFusedFwd): the first C/8 threads of every CTA turn the fp64 accumulators into scale / shift for
@@ -1210,17 +1215,17 @@ void launch_conv0_wgrad(const void* x, int x_is_u8, const act_t* dy, float* dw, 
 #ifndef DDPT_ACT_F16
 void launch_bn_finalize(const float* partials, int num_partials, int channels, double count, const float* gamma,
                         const float* beta, float eps, float momentum, BnCoeffs out, float* running_mean,
-                        float* running_var, long long* nbt, cudaStream_t s) {
+                        float* running_var, long long* nbt, const float* conv_bias, cudaStream_t s) {
   launch_pdl(bn_finalize_kernel, dim3((channels + 31) / 32), dim3(32 * kFinGroups), 0, s, partials, num_partials, channels, count, gamma, beta,
-                                                                eps, momentum, out, running_mean, running_var, nbt);
+                                                                eps, momentum, out, running_mean, running_var, nbt, conv_bias);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                            const float* running_var, float eps, int channels, float* scale, float* shift,
-                           cudaStream_t s) {
+                           const float* conv_bias, cudaStream_t s) {
   launch_pdl(bn_eval_coeffs_kernel, dim3((channels + 127) / 128), dim3(128), 0, s, gamma, beta, running_mean, running_var, eps, channels,
-                                                               scale, shift);
+                                                               scale, shift, conv_bias);
   DDPT_CUDA_CHECK(cudaGetLastError());
 }
 

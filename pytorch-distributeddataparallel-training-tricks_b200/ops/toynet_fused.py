@@ -115,6 +115,9 @@ class FusedToyNet:
         self._det_ws: Optional[torch.Tensor] = None
         self.dgrad64_pair = os.environ.get("DDPT_DGRAD64_PAIR", "0") == "1"
         self.fuse_conv0_bn = os.environ.get("DDPT_FUSE_CONV0_BN", "1") != "0"
+        # tensor-core layers leave their bias to the BatchNorm statistics kernels (see _folds_bias); DDPT_FOLD_CONV_BIAS=0
+        # keeps the add in the GEMM epilogues
+        self.fold_bias = os.environ.get("DDPT_FOLD_CONV_BIAS", "1") != "0"
         self.dense_splitk = int(os.environ.get("DDPT_DENSE_SPLITK", "4"))   # measured: 128 x 128 tiles x 4 splits 27.5 us, 64-wide tiles unsplit 35.8 us
         self.fused_stats = (compute != "fp8" and not deterministic()
                             and os.environ.get("DDPT_FUSED_BN_STATS", "0") == "1")
@@ -199,16 +202,28 @@ class FusedToyNet:
         return [self._grad_view(arena.grad_arena, arena.offset_of[i], p) for i, p in enumerate(self.params)]
 
     # -- forward ---------------------------------------------------------------------------------------
-    def _bn_coeffs(self, k: int, ws: _Workspace, train: bool, rows: int, count: float) -> None:
+    def _bn_coeffs(self, k: int, ws: _Workspace, train: bool, rows: int, count: float,
+                   conv_bias: Optional[torch.Tensor] = None) -> None:
+        """``conv_bias``: the producing GEMM left its bias out (see :meth:`_folds_bias`); the statistics kernels put it back
+        where it is observable -- running_mean in training, the shift of the running statistics in eval."""
         bn = self.bn[k]
         if train:
             self.ext.bn_finalize(ws.part, rows, count, bn.weight, bn.bias, _EPS, _MOMENTUM, ws.coef[k],
-                                 bn.running_mean, bn.running_var, bn.num_batches_tracked)
+                                 bn.running_mean, bn.running_var, bn.num_batches_tracked, conv_bias)
         else:
-            self.ext.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, _EPS, ws.coef[k])
+            self.ext.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, _EPS, ws.coef[k], conv_bias)
+
+    def _folds_bias(self, fused: bool, fp8_layer: bool) -> bool:
+        """A bias in front of a BatchNorm is a per-channel constant the normalisation removes again: the output, the ReLU
+        mask and every gradient are those of the bias-free convolution (and d loss / d bias is exactly zero).  The
+        tensor-core layers therefore skip the add -- 64 loads + 64 adds per thread and tile in an epilogue that paces
+        conv.3's forward (profiles/ncu_r2_fwd3_halo_step.txt) -- store bias-free activations, and hand the bias to the
+        statistics kernels.  Not with the fp64-accumulator statistics (opt-in) or the MXFP8 layers, whose passes do not
+        take the bias."""
+        return self.fold_bias and not fused and not fp8_layer
 
     def _bn_act(self, k: int, ws: _Workspace, train: bool, fused: bool, rows: int, count: float, pool: bool,
-                flatten: bool, q) -> None:
+                flatten: bool, q, conv_bias: Optional[torch.Tensor] = None) -> None:
         """BatchNorm (batch or running statistics) + ReLU (+ 2x2 max-pool, + flatten) of block k: y[k] -> a[k]."""
         ext, bn = self.ext, self.bn[k]
         if fused:      # the pass derives scale/shift from the accumulators itself and publishes coef / running stats
@@ -216,7 +231,7 @@ class FusedToyNet:
                              bn.weight, bn.bias, _EPS, _MOMENTUM, bn.running_mean, bn.running_var,
                              bn.num_batches_tracked)
         else:
-            self._bn_coeffs(k, ws, train, rows, count)
+            self._bn_coeffs(k, ws, train, rows, count, conv_bias)
             ext.bn_relu_pool(ws.y[k], ws.coef[k], ws.a[k], pool, flatten, q[0], q[1])
 
     def forward_impl(self, x: torch.Tensor, train: bool, target: Optional[torch.Tensor] = None,
@@ -243,18 +258,23 @@ class FusedToyNet:
         act = ws.a[0]
         for k, (pidx, h_in, c_in, c_out, pool) in enumerate(_TC_BLOCKS, start=1):
             h_out = h_in - 2
+            bias = P[pidx + 1].detach()
+            fold = self._folds_bias(fused, self.compute == "fp8" and c_in % 128 == 0)
             if self.compute == "fp8" and c_in % 128 == 0:
                 xq, xs = ws.fp8_buffers(k, act)            # written by the previous block's fused BN+ReLU(+pool) pass
                 wq, wsc = self._weight_fp8(pidx)
                 _, tiles = gemm.conv_fwd_mxfp8(xq, xs, wq, wsc, 3, 3, P[pidx + 1].detach(), False, part, ws.y[k])
             else:
-                _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, P[pidx + 1].detach(), False,
+                _, tiles = gemm.conv_fwd(act, self._weight_bf16(pidx), 3, 3, None if fold else bias, False,
                                          stat_out(k, c_out), ws.y[k])
             q = ws.fp8_buffers(k + 1, ws.a[k]) if self.compute == "fp8" else (None, None)   # consumer: conv.7 / conv.10 / dense.1
-            self._bn_act(k, ws, train, fused, 4 * tiles, batch * float(h_out * h_out), pool, k == 3, q)
+            self._bn_act(k, ws, train, fused, 4 * tiles, batch * float(h_out * h_out), pool, k == 3, q,
+                         bias if fold else None)
             act = ws.a[k]
         # dense.1 + BN1d + ReLU
         y4 = ws.y[4].view(batch, 512)
+        bias4 = P[17].detach()
+        fold4 = self._folds_bias(fused, self.compute == "fp8")
         if self.compute == "fp8":
             xq, xs = ws.fp8_buffers(4, ws.a[3])
             wq, wsc = self._weight_fp8(16)
@@ -263,13 +283,14 @@ class FusedToyNet:
         elif self.dense_splitk > 1 and not fused and batch >= 256:
             # 8 x 8 output tiles cannot fill 148 SMs and each streams K = 8192 through one SM's L2 port: split the
             # reduction over `dense_splitk` CTAs per 128 x 128 tile (fp32 slabs), fold + pack + statistics in one pass
-            _, rows4 = gemm.linear_fwd_splitk(ws.a[3], self._weight_bf16(16), P[17].detach(), part, y4,
+            _, rows4 = gemm.linear_fwd_splitk(ws.a[3], self._weight_bf16(16), None if fold4 else bias4, part, y4,
                                               split_k=self.dense_splitk, block_n=128)
         else:
-            _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1, P[17].detach(),
-                                     False, stat_out(4, 512), y4.view(1, 1, batch, 512), block_n=64)
+            _, tiles = gemm.conv_fwd(ws.a[3].view(1, 1, batch, 8192), self._weight_bf16(16), 1, 1,
+                                     None if fold4 else bias4, False, stat_out(4, 512), y4.view(1, 1, batch, 512),
+                                     block_n=64)
             rows4 = 4 * tiles
-        self._bn_act(4, ws, train, fused, rows4, float(batch), False, False, (None, None))
+        self._bn_act(4, ws, train, fused, rows4, float(batch), False, False, (None, None), bias4 if fold4 else None)
         if not head:       # training step engine: the backward head launch also produces loss / accuracy
             return ws.logits
         # head: logits (+ fused cross-entropy metrics when a target is given and no gradient is needed here)
