@@ -5,7 +5,7 @@ import collections, glob, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "pytorch-distributeddataparallel-training-tricks_b200", "_ext", "obj")
 OUT = os.path.join(ROOT, "sass")
-KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "LDGMC", "STGMC",
+KEY = ["UTCHMMA", "UTCQMMA", "USETMAXREG", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "LDGMC", "STGMC",
        "MEMBAR", "REDG", "ATOMG", "HMMA", "LDGSTS", "SHFL", "LDG", "STG", "ST", "LD", "BAR"]
 os.makedirs(OUT, exist_ok=True)
 rows = []
@@ -27,7 +27,7 @@ for obj in sorted(glob.glob(os.path.join(OBJ, "*.cu.*.o"))):
         pdl = sum(1 for o in ops if o.startswith("ACQBULK") or o.startswith("PREEXIT"))
         rows.append((src, short, len(ops), found))
         keep = ("conv_gemm_persistent_kernel<256, false, false, 2>", "conv_gemm_persistent_kernel<256, true, false, 2>",
-                "conv_gemm_halo_kernel<128, false, true, 1, 1>", "conv_gemm_halo_kernel<64, true, true, 1, 2>",
+                "conv_gemm_halo_kernel<128, false, true, 1, 1>", "conv_dgrad_kwmerge_kernel<2>", "conv0_wgrad_tc_kernel<false>",
                 "wgrad_gemm_kernel<128>", "wgrad_multitap_kernel<64, 256>", "conv_gemm_mxfp8_kernel",
                 "twoshot_kernel<0, true>", "twoshot_kernel<1, true>", "twoshot_kernel<0, false>",
                 "oneshot_push_kernel<0, true>", "symm_broadcast_kernel<true>", "fused_lookahead_sgd_kernel")
