@@ -56,7 +56,7 @@ int64_t conv0_fwd(at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor y
 
 void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10::optional<at::Tensor> partials,
                  c10::optional<at::Tensor> bn_y, c10::optional<at::Tensor> bn_g, c10::optional<at::Tensor> bn_coeffs,
-                 c10::optional<at::Tensor> bn_bwd_coef, c10::optional<bool> tensor_core) {
+                 c10::optional<at::Tensor> bn_bwd_coef, c10::optional<bool> tensor_core, int64_t channels_per_thread) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kByte || x.scalar_type() == at::kFloat));
   need_act(dy, dy, "dy"); need(dw, at::kFloat, "dw"); need(db, at::kFloat, "db");
   const int batch = (int)(x.numel() / (28 * 28));
@@ -88,10 +88,10 @@ void conv0_wgrad(at::Tensor x, at::Tensor dy, at::Tensor dw, at::Tensor db, c10:
   }
   if (is_half(dy))
     ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, hf(dy), dw.data_ptr<float>(),
-                             db.data_ptr<float>(), part, batch, bn, cur());
+                             db.data_ptr<float>(), part, batch, bn, cur(), (int)channels_per_thread);
   else
     ddpt::launch_conv0_wgrad(x.data_ptr(), x.scalar_type() == at::kByte, bf(dy), dw.data_ptr<float>(),
-                             db.data_ptr<float>(), part, batch, bn, cur());
+                             db.data_ptr<float>(), part, batch, bn, cur(), (int)channels_per_thread);
 }
 
 // coeffs: float [4][C] = scale, shift, mean, invstd
@@ -348,7 +348,7 @@ void ddpt_bind_nn(pybind11::module_& m) {
   m.def("conv0_fwd", &conv0_fwd);
   m.def("conv0_wgrad", &conv0_wgrad, py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("db"), py::arg("partials") = py::none(),
         py::arg("bn_y") = py::none(), py::arg("bn_g") = py::none(), py::arg("bn_coeffs") = py::none(),
-        py::arg("bn_bwd_coef") = py::none(), py::arg("tensor_core") = py::none());
+        py::arg("bn_bwd_coef") = py::none(), py::arg("tensor_core") = py::none(), py::arg("channels_per_thread") = 0);
   m.def("transpose_taps", &transpose_taps);
   m.def("det_workspace_floats", []() {     // fp32 elements of the deterministic-mode partial-row workspace
     return (int64_t)std::max<int64_t>((int64_t)ddpt::conv0_wgrad_partial_rows() * 640,

@@ -31,10 +31,12 @@ struct Conv0BnFuse {
   const float* bcoef;          // [3][64] from bn_bwd_finalize
 };
 int conv0_wgrad_partial_rows();
+// channels_per_thread: 8 (8 warps per SM, 80 accumulators per thread), 4 (16 warps, 40 accumulators) or 0 = the default
+// (DDPT_CONV0_WGRAD_CH, else the measured-best one).
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __nv_bfloat16* dy, float* dw, float* db, float* partials,
-                        int batch, const Conv0BnFuse& bn, cudaStream_t s);
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s, int channels_per_thread = 0);
 // Same contract on the tensor cores (csrc/nn/conv0_wgrad_tc.cu): dW^T = dy^T . [patches | 1] as 128 x 32 x 16 tcgen05.mma
-// over operands the threads write to shared memory (dy derived from y0 / g on the fly when bn.y is set); the default.
+// over operands the threads write to shared memory (dy derived from y0 / g on the fly when bn.y is set); opt-in.
 void launch_conv0_wgrad_tc(const void* x, int x_is_u8, const void* dy, int fp16, float* dw, float* db, float* partials,
                            int batch, const Conv0BnFuse& bn, cudaStream_t s);
 
@@ -136,7 +138,7 @@ int launch_conv0_fwd(const void* x, int x_is_u8, const float* weight /*[64][9]*/
                      __half* y, float* stat_partials /*[rows][2][64] or null*/, double* stat_accum,
                      int batch, cudaStream_t s);
 void launch_conv0_wgrad(const void* x, int x_is_u8, const __half* dy, float* dw, float* db, float* partials,
-                        int batch, const Conv0BnFuse& bn, cudaStream_t s);
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s, int channels_per_thread = 0);
 void launch_bn_relu_pool(const __half* y, const float* scale, const float* shift, __half* out, int n,
                          int h, int w, int c, int pool, int flatten_chw, uint8_t* q_out, uint8_t* q_scale,
                          const BnFusedFwd& fused, cudaStream_t s);

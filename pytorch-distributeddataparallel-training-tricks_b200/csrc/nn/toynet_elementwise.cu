@@ -290,6 +290,130 @@ conv0_wgrad_kernel(const void* __restrict__ x, int x_is_u8, const act_t* __restr
   }
 }
 
+// Same contract, 4 channels per thread and 512 threads per CTA: 40 accumulators instead of 80 (~100 registers), so the
+// SM holds 16 warps instead of 8.  The 8-channel kernel is issue-bound with two warps per scheduler at ~4.9 cycles per
+// instruction (profiles/ncu_r2_conv0_wgrad.txt); twice the warps hide the FFMA / LDS latencies, at the price of twice the
+// patch loads per FFMA.  DDPT_CONV0_WGRAD_CH=4 selects it.
+constexpr int kThreads4 = 512;
+
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
+  const act2_t* p = reinterpret_cast<const act2_t*>(&v);
+  float2 a = act2_to_float2(p[0]), b = act2_to_float2(p[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+
+__global__ void __launch_bounds__(kThreads4, 1)
+conv0_wgrad4_kernel(const void* __restrict__ x, int x_is_u8, const act_t* __restrict__ dy,
+                    float* __restrict__ dw, float* __restrict__ db, float* __restrict__ partials, int batch,
+                    const Conv0BnFuse bn) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_img[kImg * kImg];
+  __shared__ float s_acc[kThreads4 / 32][kC0 * 10];        // one slot per warp: ordered block fold
+  const int cg = threadIdx.x & 15, prow = threadIdx.x >> 4;   // 16 channel groups of 4, 32 pixel rows
+  const bool fused = bn.y != nullptr;
+  float f_sc[4], f_sh[4], f_c1[4], f_k0[4], f_k1[4];
+  if (fused) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cg * 4 + j;
+      const float c1 = __ldg(bn.bcoef + c), c2 = __ldg(bn.bcoef + kC0 + c), c3 = __ldg(bn.bcoef + 2 * kC0 + c);
+      f_sc[j] = __ldg(bn.scale + c); f_sh[j] = __ldg(bn.shift + c);
+      f_c1[j] = c1;
+      f_k1[j] = c1 * __ldg(bn.invstd + c) * c3;
+      f_k0[j] = fmaf(f_k1[j], __ldg(bn.mean + c), -c1 * c2);
+    }
+  }
+  float acc[4][10];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[c][t] = 0.f;
+  for (int img = blockIdx.x; img < batch; img += gridDim.x) {
+    __syncthreads();
+    if (x_is_u8) {
+      const uint8_t* src = static_cast<const uint8_t*>(x) + (size_t)img * kImg * kImg;
+      for (int i = threadIdx.x; i < kImg * kImg / 4; i += kThreads4) {
+        uchar4 v = reinterpret_cast<const uchar4*>(src)[i];
+        s_img[4 * i] = v.x * (1.0f / 255.0f); s_img[4 * i + 1] = v.y * (1.0f / 255.0f);
+        s_img[4 * i + 2] = v.z * (1.0f / 255.0f); s_img[4 * i + 3] = v.w * (1.0f / 255.0f);
+      }
+    } else {
+      const float* src = static_cast<const float*>(x) + (size_t)img * kImg * kImg;
+      for (int i = threadIdx.x; i < kImg * kImg; i += kThreads4) s_img[i] = src[i];
+    }
+    __syncthreads();
+    constexpr int kStep = kThreads4 / 16;                    // 32 pixels per sweep of the block
+    for (int p0 = prow; p0 < kPix0; p0 += 4 * kStep) {
+      uint2 raw[4], rawy[4];                                 // four gradient vectors in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kStep;
+        if (p < kPix0) {
+          const size_t off = ((size_t)img * kPix0 + p) * kC0 + cg * 4;
+          if (fused) {
+            raw[u] = __ldg(reinterpret_cast<const uint2*>(static_cast<const act_t*>(bn.g) + off));
+            rawy[u] = __ldg(reinterpret_cast<const uint2*>(static_cast<const act_t*>(bn.y) + off));
+          } else {
+            raw[u] = __ldg(reinterpret_cast<const uint2*>(dy + off));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kStep;
+        if (p >= kPix0) continue;
+        const int oh = p / kOut0, ow = p - oh * kOut0;
+        float g[4];
+        unpack4(raw[u], g);
+        if (fused) {
+          float yv[4];
+          unpack4(rawy[u], yv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dz = fmaf(yv[j], f_sc[j], f_sh[j]) > 0.f ? g[j] : 0.f;
+            g[j] = from_act(to_act(fmaf(f_c1[j], dz, fmaf(-f_k1[j], yv[j], f_k0[j]))));
+          }
+        }
+        float in[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) in[r * 3 + q] = s_img[(oh + r) * kImg + ow + q];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+          acc[c][9] += g[c];
+        }
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      float v = acc[c][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 16);               // the two pixel rows of a warp that share a channel group
+      if ((threadIdx.x & 31) < 16) s_acc[warp][(cg * 4 + c) * 10 + t] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC0 * 10; i += kThreads4) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads4 / 32; ++w) tot += s_acc[w][i];
+    const int ch = i / 10, t = i - ch * 10;
+    if (partials != nullptr) {
+      partials[(size_t)blockIdx.x * (kC0 * 10) + (t < 9 ? ch * 9 + t : kC0 * 9 + ch)] = tot;
+    } else if (t < 9) {
+      atomicAdd(dw + ch * 9 + t, tot);
+    } else {
+      atomicAdd(db + ch, tot);
+    }
+  }
+}
+
 // out[i] (+)= sum over rows r (in order) of partials[r * ld + i]: the ordered cross-block fold of deterministic mode
 __global__ void __launch_bounds__(kThreads)
 reduce_rows_kernel(const float* __restrict__ partials, int rows, int ld, int n, float* __restrict__ out, int accumulate) {
@@ -1199,11 +1323,17 @@ int conv0_wgrad_partial_rows() { return sm_count() * 2; }
 
 #endif
 void launch_conv0_wgrad(const void* x, int x_is_u8, const act_t* dy, float* dw, float* db, float* partials,
-                        int batch, const Conv0BnFuse& bn, cudaStream_t s) {
+                        int batch, const Conv0BnFuse& bn, cudaStream_t s, int channels_per_thread) {
   // the fused variant holds 40 more per-thread constants (177 registers): one resident CTA per SM, so one CTA per SM
   const int per_sm = bn.y != nullptr ? 1 : 2;
-  const int grid = batch < sm_count() * per_sm ? batch : sm_count() * per_sm;
-  launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, partials, batch, bn);
+  int grid = batch < sm_count() * per_sm ? batch : sm_count() * per_sm;
+  static const int env_ch = std::getenv("DDPT_CONV0_WGRAD_CH") != nullptr ? std::atoi(std::getenv("DDPT_CONV0_WGRAD_CH")) : 8;
+  if ((channels_per_thread != 0 ? channels_per_thread : env_ch) == 4) {        // 4 channels per thread, one 16-warp CTA per SM
+    grid = batch < sm_count() ? batch : sm_count();
+    launch_pdl(conv0_wgrad4_kernel, dim3(grid), dim3(kThreads4), 0, s, x, x_is_u8, dy, dw, db, partials, batch, bn);
+  } else {
+    launch_pdl(conv0_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, x, x_is_u8, dy, dw, db, partials, batch, bn);
+  }
   if (partials != nullptr) {          // deterministic mode: fold the block rows in order (dw: 576 columns, db: 64)
     launch_pdl(reduce_rows_kernel, dim3((kC0 * 9 + kThreads - 1) / kThreads), dim3(kThreads), 0, s,
                (const float*)partials, grid, kC0 * 10, kC0 * 9, dw, 1);

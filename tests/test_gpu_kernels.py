@@ -442,7 +442,7 @@ def _conv0_wgrad_reference(x_f, dy_f):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("u8", [True, False])
 @pytest.mark.parametrize("det", [False, True])
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("tc", [True, False, 4])        # tensor cores / CUDA cores 8 channels per thread / 4 per thread
 def test_conv0_wgrad_kernels(ext, batch, dtype, u8, det, tc):
     g = torch.Generator(device="cuda").manual_seed(91)
     if u8:
@@ -454,7 +454,8 @@ def test_conv0_wgrad_kernels(ext, batch, dtype, u8, det, tc):
     dy = (torch.randn(batch, 26, 26, 64, device="cuda", generator=g) * 0.1).to(dtype)
     dw, db = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
     part = torch.zeros(ext.det_workspace_floats(), device="cuda") if det else None
-    ext.conv0_wgrad(x, dy, dw, db, part, tensor_core=tc)
+    kw = dict(tensor_core=False, channels_per_thread=4) if tc == 4 else dict(tensor_core=tc, channels_per_thread=8)
+    ext.conv0_wgrad(x, dy, dw, db, part, **kw)
     want_w, want_b = _conv0_wgrad_reference(x_f, dy.float())
     # dy is exact (already 16-bit); on the tensor cores x goes in as a 16-bit value + its rounding remainder:
     # fp32-accumulation accuracy either way
@@ -462,12 +463,12 @@ def test_conv0_wgrad_kernels(ext, batch, dtype, u8, det, tc):
     assert _rel_err(db, want_b) < 2e-5
     if det:
         dw2, db2 = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
-        ext.conv0_wgrad(x, dy, dw2, db2, part, tensor_core=tc)
+        ext.conv0_wgrad(x, dy, dw2, db2, part, **kw)
         assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("tc", [True, False, 4])
 def test_conv0_wgrad_fused_bn_apply(ext, dtype, tc):
     """With the BatchNorm-backward apply folded in: dy = c1 * dz + k0 - k1 * y0, dz = g where relu(bn(y0)) > 0."""
     batch = 200
@@ -489,7 +490,8 @@ def test_conv0_wgrad_fused_bn_apply(ext, dtype, tc):
     dy = (c1 * dz + k0 - k1 * yf).to(dtype).float()                 # the kernel rounds dy to the activation type
     want_w, want_b = _conv0_wgrad_reference(x.float() / 255.0, dy)
     dw, db = torch.zeros(576, device="cuda"), torch.zeros(64, device="cuda")
-    ext.conv0_wgrad(x, torch.empty_like(y0), dw, db, None, y0, gin, coeffs.view(-1), bcoef.view(-1), tensor_core=tc)
+    kw = dict(tensor_core=False, channels_per_thread=4) if tc == 4 else dict(tensor_core=tc, channels_per_thread=8)
+    ext.conv0_wgrad(x, torch.empty_like(y0), dw, db, None, y0, gin, coeffs.view(-1), bcoef.view(-1), **kw)
     # fmaf association differs from the torch expression by an ulp of the 16-bit rounding on a few elements
     assert _rel_err(dw.view(64, 9), want_w) < 2e-3, _rel_err(dw.view(64, 9), want_w)
     assert _rel_err(db, want_b) < 2e-3
