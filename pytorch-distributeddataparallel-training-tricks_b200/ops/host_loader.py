@@ -39,6 +39,8 @@ class PinnedGatherLoader:
                                               [t.data_ptr() for t in self.lbl_slots], threads)
         self.image_shape = tuple(images.shape[1:])
         self._armed = None          # (indices, num_batches) of a speculatively started epoch
+        self.epoch_starts = 0       # native start_epoch calls (own epochs + speculative ones)
+        self.adopted_epochs = 0     # epochs that found their gather already running
 
     def epoch(self, indices: torch.Tensor, num_batches: int, next_epoch=None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
         """Yield the batches of one epoch.  ``next_epoch`` (optional callable -> (indices, num_batches) or None): as soon
@@ -52,6 +54,9 @@ class PinnedGatherLoader:
         self._armed = None
         if armed is None or armed[1] != nb or armed[0].shape != idx.shape or not torch.equal(armed[0], idx):
             self._native.start_epoch(idx.data_ptr(), idx.numel(), nb)
+            self.epoch_starts += 1
+        else:
+            self.adopted_epochs += 1          # the speculative gather started at the end of the previous epoch is this epoch
         pending = []            # (slot, event) whose H2D copy may still be in flight
         while True:
             slot, rows = self._native.next()
@@ -79,4 +84,5 @@ class PinnedGatherLoader:
             if nxt is not None:
                 nidx = nxt[0].to(torch.int64).contiguous()
                 self._native.start_epoch(nidx.data_ptr(), nidx.numel(), int(nxt[1]))      # workers start filling slots now
+                self.epoch_starts += 1
                 self._armed = (nidx, int(nxt[1]))

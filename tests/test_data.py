@@ -106,8 +106,12 @@ def test_native_loader_speculative_next_epoch_and_restart():
             assert torch.equal(img.view(-1, 28, 28), images[sel]) and torch.equal(lbl, labels[sel])
 
     check(run(perms[0], perms[1]), perms[0])
-    gathered = loader._native.batches_gathered()
+    assert (loader.epoch_starts, loader.adopted_epochs) == (2, 0)        # epoch 0 + the speculative start of epoch 1
     check(run(perms[1], perms[2]), perms[1])                  # adopted: no restart, the head of the epoch was already gathered
-    assert loader._native.batches_gathered() >= gathered + 8
+    assert (loader.epoch_starts, loader.adopted_epochs) == (3, 1)        # only epoch 2's speculation was started
     check(run(perms[3]), perms[3])                            # speculation (perms[2]) discarded, fresh start
+    assert (loader.epoch_starts, loader.adopted_epochs) == (4, 1)
     check(run(perms[0]), perms[0])
+    assert (loader.epoch_starts, loader.adopted_epochs) == (5, 1)
+    # every batch of the four epochs was gathered; speculative batches of the discarded epoch come on top (at most `depth`)
+    assert 32 <= loader._native.batches_gathered() <= 32 + 4
