@@ -13,7 +13,8 @@ import pytest
 from conftest import ROOT
 
 CSRC = os.path.join(ROOT, "pytorch-distributeddataparallel-training-tricks_b200", "csrc")
-GEMM_SOURCES = ["nn/conv_gemm_persistent.cu", "nn/conv_gemm_halo.cu", "nn/wgrad_gemm_multitap.cu", "nn/wgrad_gemm.cu"]
+GEMM_SOURCES = ["nn/conv_gemm_persistent.cu", "nn/conv_gemm_halo.cu", "nn/wgrad_gemm_multitap.cu", "nn/wgrad_gemm.cu",
+                "nn/conv_dgrad_kwmerge.cu", "nn/conv0_wgrad_tc.cu"]
 
 
 @pytest.mark.parametrize("src", GEMM_SOURCES)
